@@ -1,0 +1,2 @@
+"""Empty stand-in package: not touched by the hot path (oracle/make_golden.py only)."""
+from . import display  # noqa: F401

@@ -1,0 +1,74 @@
+"""Named test cases shared by oracle/make_golden.py (reference run) and the tests (oracle / CUDA runs)."""
+from __future__ import annotations
+
+import numpy as np
+
+from mcmc_gpu_b200 import synthetic as syn
+
+MATERN = dict(syn.RF_KW)
+
+# Each trajectory case is one `chain_crf.run(n_iter, RF, only_save_last_bed=True)` of the reference.
+TRAJECTORY_CASES = {
+    # BASELINE.json config 1 at reduced length: the tutorial configuration, SURVEY §8c anchor
+    # (final loss 348.2912467039959 at n_iter=500).
+    "tutorial200": dict(H=200, W=200, n_iter=500, rf_seed=7, chain_seed=11, rf_kw=MATERN, blocks=(50, 80, 50, 80),
+                        logistic=(2.0, 0.0, 6.0, 1.0), max_dist=30e3, sigma_mc=5.0, update_in_region=True,
+                        block_type="CRF_weight"),
+    # Non-square grid, small blocks clipped by every edge, taper that is NOT zero on the rim (stale-ring quirk),
+    # nugget noise, anisotropic draw order, plain 'RF' update over the whole map.
+    "ragged_rf": dict(H=72, W=90, n_iter=400, rf_seed=3, chain_seed=5,
+                      rf_kw=dict(range_min_x=2e3, range_max_x=9e3, range_min_y=3e3, range_max_y=8e3, scale_min=20.0,
+                                 scale_max=60.0, nugget_max=4.0, model_name="Exponential", isotropic=False,
+                                 smoothness=None),
+                      blocks=(10, 30, 12, 26), logistic=(1.0, 0.5, 6.0, 0.0), max_dist=3e3, sigma_mc=10.0,
+                      update_in_region=False, block_type="RF"),
+    # Thin ice: the thickness guard (loss = inf) fires on part of the proposals; Gaussian model.
+    "thin_ice": dict(H=96, W=80, n_iter=400, rf_seed=21, chain_seed=22,
+                     rf_kw=dict(range_min_x=3e3, range_max_x=10e3, range_min_y=3e3, range_max_y=10e3, scale_min=60.0,
+                                scale_max=200.0, nugget_max=0.0, model_name="Gaussian", isotropic=True,
+                                smoothness=None),
+                     blocks=(16, 32, 16, 32), logistic=(2.0, 0.0, 6.0, 1.0), max_dist=4e3, sigma_mc=40.0,
+                     update_in_region=True, block_type="CRF_weight", thin=True),
+}
+
+
+def build_case_grids(case: dict) -> dict:
+    g = syn.make_grids(case["H"], case["W"])
+    if case.get("thin"):
+        # pull the surface down to ~100 m above the bed so about half the proposals hit non-positive thickness
+        g["surf"] = g["bed0"] + 100.0 + 10.0 * np.sin(g["xx"] / 7e3)
+        g["highvel_mask"] = ((np.hypot(g["velx"], g["vely"]) > 60.0) | (g["yy"] < 15e3)).astype(np.int64)
+    return g
+
+
+FIELD_CASES = {
+    "matern_iso": dict(rf_kw=MATERN, seed=101, res=500.0, shapes=[(50, 56), (64, 64), (72, 80), (80, 50)]),
+    "gauss_aniso_nug": dict(rf_kw=dict(range_min_x=5e3, range_max_x=20e3, range_min_y=8e3, range_max_y=30e3,
+                                       scale_min=10.0, scale_max=30.0, nugget_max=2.5, model_name="Gaussian",
+                                       isotropic=False, smoothness=None), seed=102, res=250.0,
+                            shapes=[(20, 24), (30, 18), (58, 22)]),
+    "expo_iso": dict(rf_kw=dict(range_min_x=1e3, range_max_x=4e3, range_min_y=1e3, range_max_y=4e3, scale_min=1.0,
+                                scale_max=2.0, nugget_max=0.0, model_name="Exponential", isotropic=True,
+                                smoothness=None), seed=103, res=100.0, shapes=[(14, 66), (26, 26)]),
+}
+
+
+def residual_case_inputs() -> dict:
+    """A ragged 37x53 grid with NaN holes, a mask with values {0,1} and rough random fields."""
+    H, W = 37, 53
+    g = np.random.default_rng(2024)
+    res = 125.0
+    xx, yy = np.meshgrid(np.arange(W) * res, np.arange(H) * res)
+    surf = 1500.0 + 300.0 * g.standard_normal((H, W))
+    bed = surf - 800.0 + 100.0 * g.standard_normal((H, W))
+    velx = 200.0 * g.standard_normal((H, W))
+    vely = 150.0 * g.standard_normal((H, W))
+    dhdt = g.standard_normal((H, W))
+    smb = g.standard_normal((H, W))
+    bed[5, 7] = np.nan
+    velx[20, 0] = np.nan
+    smb[36, 52] = np.nan
+    mask = (g.random((H, W)) < 0.6).astype(np.int64)
+    mask[5, 6] = 1
+    return dict(xx=xx, yy=yy, bed=bed, surf=surf, velx=velx, vely=vely, dhdt=dhdt, smb=smb, mask=mask,
+                resolution=res, sigma_mc=2.5)
