@@ -1,0 +1,155 @@
+/* gmc.h — C ABI of libgmc.so: the B200 (sm_100a) many-chain MCMC step of gstatsMCMC.
+ *
+ * The reference (tylerrleee/mcmc-gpu, pure Python) has no FFI layer; its boundary for this path is the Python API
+ * of gstatsMCMC/MCMC.py and gstatsMCMC/Topography.py.  Each entry point below names the reference code it replaces
+ * (file:line into the reference tree).  The Python mirror of that API (mcmc_gpu_b200/MCMC.py, Topography.py) binds
+ * these symbols with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (GMC_OK) or a negative gmc_status; gmc_last_error() gives the thread-local message;
+ *     nothing throws across the boundary.
+ *   - arrays are float64, row-major, chains outermost: bed[C][H][W]; masks are uint8 holding 0/1.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (torch.Tensor.data_ptr()).  "any" pointers may be
+ *     host or device (copied with cudaMemcpyDefault during setup calls).
+ *   - all compute calls are asynchronous on the cudaStream_t passed as `stream` (void*; NULL = legacy default).
+ *   - a context is bound to one device and is not thread-safe: one context per GPU per process.
+ *   - there is no CPU fallback: without a usable CUDA device every call fails with GMC_ECUDA.
+ */
+#ifndef GMC_H_
+#define GMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GMC_API __attribute__((visibility("default")))
+#else
+#define GMC_API
+#endif
+
+typedef struct gmc_ctx gmc_ctx;
+
+typedef enum gmc_status {
+    GMC_OK = 0,
+    GMC_EINVAL = -1,       /* bad argument value / NULL pointer                          */
+    GMC_ESHAPE = -2,       /* shape mismatch (chains > capacity, block larger than grid) */
+    GMC_ECUDA = -3,        /* CUDA runtime error, or no device                           */
+    GMC_ENCCL = -4,        /* NCCL error or libnccl not loadable                         */
+    GMC_EUNSUPPORTED = -5, /* valid in the reference but not implemented here            */
+    GMC_ESTATE = -6        /* call order: set_static / set_field_model / set_blocks first */
+} gmc_status;
+
+/* covariance model of the proposal field: RandField.model_name, MCMC.py:496-500 */
+typedef enum gmc_model { GMC_GAUSSIAN = 0, GMC_EXPONENTIAL = 1, GMC_MATERN = 2 } gmc_model;
+
+GMC_API const char* gmc_last_error(void);
+GMC_API int gmc_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+
+/* One context = one grid shape on one device, shared by up to max_chains chains.
+ * Replaces the per-process chain object state of init_lsc_chain_by_instance (MCMC.py:359-379). */
+GMC_API int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chains);
+GMC_API int gmc_destroy(gmc_ctx* ctx);
+
+/* Chain-independent inputs (identical for all chains in the reference too: largeScaleChain_multiprocessing.py:51-57).
+ *   surf, velx, vely, dhdt, smb : [H][W] f64 (any)               chain.__init__, MCMC.py:808-845
+ *   gate_mask  [H][W] u8 (any)  : region_mask when update_in_region else grounded_ice_mask; cells a proposal may
+ *                                 change, guard cells and resampled_times increment   MCMC.py:1287-1290,1324-1329,1349-1352
+ *   mc_mask    [H][W] u8 (any)  : mc_region_mask of set_loss_type                    MCMC.py:1004-1007,1041
+ *   centre_cells [n] i32 (any)  : linear indices (row*W+col) the block centre is drawn from (cells with
+ *                                 region_mask==1); NULL/0 = whole grid                MCMC.py:1253-1261
+ *   crf_weight [H][W] f64 (any) : set_crf_data_weight; NULL selects block_type 'RF'  MCMC.py:1124-1134,1279-1282
+ *   resolution, sigma_mc        : chain.resolution, set_loss_type(sigma_mc)           MCMC.py:1016 */
+GMC_API int gmc_set_static(gmc_ctx* ctx, const double* surf, const double* velx, const double* vely, const double* dhdt,
+                   const double* smb, const uint8_t* gate_mask, const uint8_t* mc_mask, const int32_t* centre_cells,
+                   int64_t n_centre_cells, const double* crf_weight, double resolution, double sigma_mc);
+
+/* RandField.__init__ parameters, MCMC.py:462-510.  smoothness is ignored unless model == GMC_MATERN. */
+GMC_API int gmc_set_field_model(gmc_ctx* ctx, int model, double smoothness, int isotropic, double range_min_x,
+                        double range_max_x, double range_min_y, double range_max_y, double scale_min,
+                        double scale_max, double nugget_max);
+
+/* RandField.set_block_sizes / get_edge_masks, MCMC.py:524-623.
+ *   pair_w[i], pair_h[i] : RandField.pairs[0][i], pairs[1][i] (even, >= 2); the field of pair i is [pair_h][pair_w]
+ *   edge_masks (any)     : the n_pairs tapers concatenated, pair i at offsets[i], row-major [pair_h][pair_w]
+ *   field_resolution     : RandField.resolution (spacing of the fftfreq grid, MCMC.py:221-222) */
+GMC_API int gmc_set_blocks(gmc_ctx* ctx, int n_pairs, const int32_t* pair_w, const int32_t* pair_h, const double* edge_masks,
+                   const int64_t* offsets, double field_resolution);
+
+/* ---- A1/A2: residual and loss ------------------------------------------------------------------------------- */
+
+/* Topography.get_mass_conservation_residual (Topography.py:592-600) for C beds at once.
+ * bed, res_out: dev [C][H][W].  Needs gmc_set_static. */
+GMC_API int gmc_residual(gmc_ctx* ctx, const double* bed, double* res_out, int C, void* stream);
+
+/* Fused residual + chain.loss (Topography.py:592-600 + MCMC.py:1041): res_out may be NULL.
+ * loss_out: dev [C] = nansum(res[mc_mask==1]^2) / (2 sigma_mc^2); ssq_out (dev [C], may be NULL) = the nansum. */
+GMC_API int gmc_residual_loss(gmc_ctx* ctx, const double* bed, double* res_out, double* loss_out, double* ssq_out, int C,
+                      void* stream);
+
+/* chain.loss (MCMC.py:1021-1044) on given residuals: res dev [C][H][W] -> loss_out dev [C] (ssq_out optional). */
+GMC_API int gmc_loss(gmc_ctx* ctx, const double* res, double* loss_out, double* ssq_out, int C, void* stream);
+
+/* ---- A3/A4: proposal field ---------------------------------------------------------------------------------- */
+
+/* spectral_synthesis_field (+ edge taper of get_rfblock when apply_taper), MCMC.py:176-254, 742-778, for n fields.
+ *   pair[n] i32 dev        : block-size index of each field
+ *   scale[n], nug[n], range_x[n], range_y[n] f64 dev : the sampled parameters (scale already divided by 3)
+ *   z_re, z_im, z_nug      : dev [n][stride] unit normals laid out [pair_h][pair_w] per field, or all NULL to draw
+ *                            them from Philox streams keyed by seeds[n] (u64 dev) at iteration `iter`
+ *   f_out                  : dev [n][stride], field i written row-major [pair_h][pair_w] at f_out + i*stride */
+GMC_API int gmc_field_spectral(gmc_ctx* ctx, int n, const int32_t* pair, const double* scale, const double* nug,
+                       const double* range_x, const double* range_y, const double* z_re, const double* z_im,
+                       const double* z_nug, const uint64_t* seeds, uint64_t iter, int apply_taper, double* f_out,
+                       int64_t stride, void* stream);
+
+/* ---- A6: Metropolis step ------------------------------------------------------------------------------------ */
+
+/* One chain_crf.run loop body (MCMC.py:1263-1360) for C chains with the proposal injected:
+ *   bed, mcres : dev [C][H][W] state (updated in place on accept);  ssq : dev [C] nansum state (loss*2 sigma^2)
+ *   f          : dev [C][f_stride], chain c's tapered field [h][w] row-major at f + c*f_stride (the value
+ *                RandField.get_rfblock returns);  hw : dev [C][2] i32 = f.shape;  centre : dev [C][2] i32 = (indexx, indexy)
+ *   u          : dev [C] uniforms of MCMC.py:1336;  hmax, wmax : upper bounds of hw (size the shared-memory tile)
+ *   accepted_out : dev [C] u8;  loss_out : dev [C] loss after the decision;  loss_next_out : dev [C] candidate loss (may be NULL)
+ *   resampled  : dev [C][H][W] i32 accepted-block coverage counts, or NULL (MCMC.py:1349-1352, times the mask value) */
+GMC_API int gmc_step_injected(gmc_ctx* ctx, double* bed, double* mcres, double* ssq, const double* f, int64_t f_stride,
+                      const int32_t* hw, const int32_t* centre, const double* u, int hmax, int wmax,
+                      uint8_t* accepted_out, double* loss_out, double* loss_next_out, int32_t* resampled, int C,
+                      void* stream);
+
+/* n_steps fused free-running iterations for C chains (proposal synthesis + step on device, no host round trips).
+ *   seeds  : dev [C] u64 per-chain Philox keys (the reference's rng_seeds, largeScaleChain_multiprocessing.py:55-57)
+ *   iter0  : index of the first iteration (Philox counter; makes runs resumable and independent of GPU count)
+ *   loss_cache, step_cache (f64 / u8, dev [C][cache_stride]) and blocks_cache (i32 dev [C][cache_stride][4] =
+ *   indexx, indexy, h, w) receive entries [iter0 - cache_iter0 + k] for step k; any may be NULL      MCMC.py:1163-1170
+ *   resync_every : recompute ssq from the tracked mcres every this many iterations (0 = never)      */
+GMC_API int gmc_run(gmc_ctx* ctx, double* bed, double* mcres, double* ssq, const uint64_t* seeds, uint64_t iter0, int n_steps,
+            double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache, int64_t cache_stride, int64_t cache_offset,
+            int32_t* resampled, int resync_every, int C, void* stream);
+
+/* ---- ensemble statistics (new) ---------------------------------------------------------------- */
+
+/* Local part of the posterior mean/variance: sum_out[H][W] = sum_c (bed_c - ref), sumsq_out = sum_c (bed_c - ref)^2. */
+GMC_API int gmc_ensemble_moments(gmc_ctx* ctx, const double* bed, const double* ref_bed, double* sum_out, double* sumsq_out,
+                         int C, void* stream);
+
+/* In-place SUM all-reduce of the two [H][W] moment arrays and count[1] over an existing ncclComm_t (the only
+ * collective on the path).  libnccl.so.2 is resolved at run time from the process (torch ships it). */
+GMC_API int gmc_allreduce_moments(gmc_ctx* ctx, void* nccl_comm, double* sum, double* sumsq, double* count, void* stream);
+
+/* ---- introspection for tests and bench ---------------------------------------------------------------------- */
+
+/* Number of kernel launches issued through this context since creation. */
+GMC_API int64_t gmc_launch_count(const gmc_ctx* ctx);
+/* Dynamic shared memory (bytes) and threads per CTA of the fused step kernel for the current block table. */
+GMC_API int gmc_step_kernel_info(const gmc_ctx* ctx, int* smem_bytes, int* threads, int* ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMC_H_ */

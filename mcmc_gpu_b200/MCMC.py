@@ -1,0 +1,540 @@
+"""Host-side mirror of the reference's chain API (gstatsMCMC/MCMC.py) over libgmc's CUDA kernels.
+
+Same class names, constructor/setter signatures, return tuples and error behaviour as the reference for the
+large-scale chain path (`RandField` MCMC.py:433, `chain` :780, `chain_crf` :1083, `spectral_synthesis_field` :176);
+every array operation of the hot loop runs on the GPU through the C ABI in include/gmc.h.  Differences, all forced by
+the design: random numbers come from per-chain counter-based Philox streams on the device instead of
+numpy PCG64 on the host (statistically equivalent; bit parity is defined under injected proposals, `replay=`), and
+`run_many` / `ChainBatch` add the batched many-chain form that the reference gets from one process per chain.
+"""
+from __future__ import annotations
+
+import numbers
+import sys
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, GmcError, GmcShapeError  # noqa: F401
+
+_MASK64 = (1 << 64) - 1
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _MASK64
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _MASK64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _MASK64
+    return z ^ (z >> 31)
+
+
+def philox_key(chain_seed: int, rf_seed: int | None = None) -> int:
+    """64-bit Philox key of one chain.  The reference seeds chain.rng and RF.rng with the same integer in its
+    drivers (MCMC.py:371,397); when they differ both enter the key."""
+    k = _splitmix64(int(chain_seed) & _MASK64)
+    if rf_seed is not None and int(rf_seed) != int(chain_seed):
+        k ^= _splitmix64((int(rf_seed) & _MASK64) ^ 0xA5A5A5A5A5A5A5A5)
+    return k
+
+
+def keys_tensor(keys, device):
+    """uint64 Philox keys -> int64 torch tensor with the same bit patterns (torch has no uint64 arithmetic)."""
+    import torch
+    return torch.as_tensor(np.array([int(k) & _MASK64 for k in keys], dtype=np.uint64).view(np.int64)).to(device)
+
+
+def _seed_to_int(rng_seed, what):
+    """None | int | numpy Generator -> integer seed (same accepted types as MCMC.py:484-491, 1057-1064)."""
+    if rng_seed is None:
+        return int(np.random.SeedSequence().generate_state(1, dtype=np.uint64)[0]), np.random.default_rng()
+    if isinstance(rng_seed, numbers.Integral) and not isinstance(rng_seed, bool):
+        return int(rng_seed), np.random.default_rng(seed=int(rng_seed))
+    if isinstance(rng_seed, np.random.Generator):
+        # derive the device key from the generator without disturbing it
+        state = rng_seed.bit_generator.state
+        probe = np.random.Generator(type(rng_seed.bit_generator)())
+        probe.bit_generator.state = state
+        return int(probe.integers(0, 2 ** 63 - 1)), rng_seed
+    raise ValueError("Seed should be an integer, a NumPy random Generator, or None")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# RandField                                                                                   reference MCMC.py:433-778
+# ------------------------------------------------------------------------------------------------------------------
+class RandField:
+    """Parameters of the block random-field proposal (reference MCMC.py:433).  Holds configuration only; fields
+    are synthesised on the GPU (K1) inside `chain_crf.run`, or one at a time through `get_rfblock()`."""
+
+    def __init__(self, range_min_x, range_max_x, range_min_y, range_max_y, scale_min, scale_max, nugget_max, model_name,
+                 isotropic, smoothness=None, rng_seed=None):
+        self.rng_seed_int, self.rng = _seed_to_int(rng_seed, "RandField")
+        if (range_max_x < range_min_x) or (range_max_y < range_min_y):
+            print("the maximum range must be greater to equal to the minimum range")
+        self.range_min_x, self.range_max_x = range_min_x, range_max_x
+        self.range_min_y, self.range_max_y = range_min_y, range_max_y
+        self.scale_min, self.scale_max, self.nugget_max = scale_min, scale_max, nugget_max
+        if model_name not in ("Gaussian", "Exponential", "Matern"):
+            raise Exception("please put in a valid model_name, including Gaussian, Exponential, and Matern")
+        if model_name == "Matern" and smoothness is None:
+            raise Exception("a smoothness value must be defined if model name is Matern")
+        self.smoothness = smoothness
+        self.model_name = model_name
+        self.isotropic = isotropic
+        self._draws = 0          # Philox iteration counter of stand-alone get_rfblock() calls
+        self._ctx = None
+
+    def set_generation_method(self, spectral):
+        """True: FFT spectral synthesis (the only method on the GPU path).  The reference's other branch calls the
+        un-vendored gstools RandMeth generator with an unseeded RNG (MCMC.py:625-687)."""
+        self.spectral = spectral
+
+    def set_block_sizes(self, min_block_x, max_block_x, min_block_y, max_block_y, steps=5):
+        self.min_block_x, self.max_block_x = min_block_x, max_block_x
+        self.min_block_y, self.max_block_y = min_block_y, max_block_y
+        self.steps = steps
+        self.pairs = self.get_block_sizes()
+        self._ctx = None
+
+    def get_block_sizes(self):
+        """[2, steps^2] int array: row 0 widths, row 1 heights, forced even (MCMC.py:568-581)."""
+        width = np.linspace(self.min_block_x, self.max_block_x, self.steps, dtype=int)
+        height = np.linspace(self.min_block_y, self.max_block_y, self.steps, dtype=int)
+        w, h = np.meshgrid(width, height)
+        return np.array([(w // 2 * 2).flatten(), (h // 2 * 2).flatten()])
+
+    def set_weight_param(self, logis_func_L, logis_func_x0, logis_func_k, logis_func_offset, max_dist, resolution):
+        if not hasattr(self, "pairs"):
+            raise Exception("It seems like the set_block_sizes has not been called yet before calling set_weight_param")
+        self.logistic_param = [logis_func_L, logis_func_x0, logis_func_k, logis_func_offset]
+        self.max_dist = max_dist
+        self.resolution = resolution
+        self.edge_masks = self.get_edge_masks()
+        self._ctx = None
+
+    def _logistic(self, dist):
+        L, x0, k, offset = self.logistic_param
+        scaled = np.where(dist > self.max_dist, 1, dist / self.max_dist)
+        return L / (1 + np.exp(-k * (scaled - x0))) - offset
+
+    def get_edge_masks(self):
+        """Taper of each block size: logistic of the distance to the block rim (MCMC.py:583-623).  The rim is the
+        full border, so the nearest-rim distance is the smallest of the four axis distances (what the reference's
+        KDTree query returns, without the tree)."""
+        if not hasattr(self, "pairs"):
+            raise Exception("It seems like the set_block_sizes has not been called yet before calling get_edge_mask")
+        masks = []
+        for i in range(self.pairs.shape[1]):
+            bw, bh = int(self.pairs[0, i]), int(self.pairs[1, i])
+            px = np.arange(bw) * self.resolution
+            py = np.arange(bh) * self.resolution
+            dx = np.minimum(px - px[0], px[-1] - px)
+            dy = np.minimum(py - py[0], py[-1] - py)
+            masks.append(self._logistic(np.minimum(dy[:, None], dx[None, :])))
+        return masks
+
+    def get_crf_weight(self, xx, yy, cond_data_mask):
+        """(weight, dist, dist_rescale, dist_logi): conditioning weight, 0 at data cells (MCMC.py:689-714).
+        One-time setup, outside the hot path; the nearest-data distance uses scipy's KD-tree like the reference."""
+        from scipy.spatial import cKDTree
+        sel = np.asarray(cond_data_mask) == 1
+        tree = cKDTree(np.column_stack([xx[sel], yy[sel]]))
+        dist = tree.query(np.column_stack([xx.ravel(), yy.ravel()]))[0].reshape(xx.shape)
+        return self.get_crf_weight_from_dist(xx, yy, dist)
+
+    def get_crf_weight_from_dist(self, xx, yy, dist):
+        """Same, from a precomputed distance map (MCMC.py:716-740)."""
+        scaled = np.where(dist > self.max_dist, 1, dist / self.max_dist)
+        logi = self._logistic(dist)
+        return logi - np.min(logi), dist, scaled, logi
+
+    # ---- stand-alone field generation on the GPU --------------------------------------------------------------
+    def _field_ctx(self):
+        if self._ctx is None:
+            hmax, wmax = int(self.pairs[1].max()), int(self.pairs[0].max())
+            ctx = Context(max(hmax, 2), max(wmax, 2), 1)
+            ctx.set_field_model(self.model_name, self.smoothness, self.isotropic, self.range_min_x, self.range_max_x,
+                                self.range_min_y, self.range_max_y, self.scale_min, self.scale_max, self.nugget_max)
+            ctx.set_blocks(self.pairs, self.edge_masks, self.resolution)
+            self._ctx = ctx
+        return self._ctx
+
+    def _require_spectral(self):
+        if not getattr(self, "spectral", True):
+            raise NotImplementedError("spectral=False selects the gstools RandMeth generator (MCMC.py:625-687), which is "
+                                      "an un-vendored dependency with an unseeded RNG in the reference; only the spectral "
+                                      "method is implemented on the GPU path")
+
+    def get_rfblock(self):
+        """One tapered proposal field f = field * edge_mask (MCMC.py:742-778), synthesised by kernel K1."""
+        import torch
+        self._require_spectral()
+        ctx = self._field_ctx()
+        dev = ctx.device
+        g = self.rng
+        pick = int(g.integers(low=0, high=self.pairs.shape[1], size=1)[0])
+        scale = g.uniform(self.scale_min, self.scale_max) / 3.0
+        nug = g.uniform(0.0, self.nugget_max)
+        if not self.isotropic:
+            rx = g.uniform(self.range_min_x, self.range_max_x)
+            ry = g.uniform(self.range_min_y, self.range_max_y)
+        else:
+            rx = ry = g.uniform(self.range_min_x, self.range_max_x)
+        bw, bh = int(self.pairs[0, pick]), int(self.pairs[1, pick])
+        out = torch.empty((1, ctx.max_h * ctx.max_w), dtype=torch.float64, device=dev)
+
+        def t(v, dt=torch.float64):
+            return torch.tensor([v], dtype=dt, device=dev)
+        seeds = keys_tensor([philox_key(self.rng_seed_int)], dev)
+        ctx.field_spectral(t(pick, torch.int32), t(scale), t(nug), t(rx), t(ry), out, seeds=seeds, iteration=self._draws,
+                           apply_taper=True)
+        self._draws += 1
+        return out[0, :bh * bw].reshape(bh, bw).cpu().numpy()
+
+
+def spectral_synthesis_field(RF, shape, res=1.0, *, draws=None):
+    """2-D Gaussian random field by spectral synthesis on the GPU (reference MCMC.py:176-254).
+
+    With `draws=None` the parameters come from RF.rng exactly like the reference (scale, nug, range[, range_y]) and the
+    normals from the device Philox stream.  `draws=dict(scale, nug, range_x, range_y, z_re, z_im, z_nug)` injects
+    every random input, which makes the result comparable to the reference to ~1e-13 (tests/test_gpu_field.py).
+    """
+    import torch
+    ny, nx = shape
+    ctx = Context(max(ny, 2), max(nx, 2), 1)
+    ctx.set_field_model(RF.model_name, RF.smoothness, RF.isotropic, RF.range_min_x, RF.range_max_x, RF.range_min_y,
+                        RF.range_max_y, RF.scale_min, RF.scale_max, RF.nugget_max)
+    ctx.set_blocks(np.array([[nx], [ny]]), [np.ones((ny, nx))], res)
+    dev = ctx.device
+    if draws is None:
+        g = RF.rng
+        scale = g.uniform(RF.scale_min, RF.scale_max) / 3.0
+        nug = g.uniform(0.0, RF.nugget_max)
+        if not RF.isotropic:
+            rx = g.uniform(RF.range_min_x, RF.range_max_x)
+            ry = g.uniform(RF.range_min_y, RF.range_max_y)
+        else:
+            rx = ry = g.uniform(RF.range_min_x, RF.range_max_x)
+        z = {}
+    else:
+        scale, nug, rx, ry = draws["scale"], draws["nug"], draws["range_x"], draws["range_y"]
+        z = {k: torch.as_tensor(np.ascontiguousarray(draws[k], dtype=np.float64).reshape(1, ny * nx), device=dev)
+             for k in ("z_re", "z_im", "z_nug")}
+
+    def t(v, dt=torch.float64):
+        return torch.tensor([v], dtype=dt, device=dev)
+    out = torch.empty((1, ny * nx), dtype=torch.float64, device=dev)
+    seeds = keys_tensor([philox_key(getattr(RF, "rng_seed_int", 0))], dev)
+    it = getattr(RF, "_draws", 0)
+    ctx.field_spectral(t(0, torch.int32), t(scale), t(nug), t(rx), t(ry), out, seeds=None if z else seeds, iteration=it,
+                       apply_taper=False, **z)
+    if not z:
+        RF._draws = it + 1
+    res_np = out.reshape(ny, nx).cpu().numpy()
+    ctx.close()
+    return res_np
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# chain base class                                                                            reference MCMC.py:780-1081
+# ------------------------------------------------------------------------------------------------------------------
+class chain:
+    def __init_func__(self):
+        return
+
+    def __init__(self, xx, yy, initial_bed, surf, velx, vely, dhdt, smb, cond_bed, data_mask, grounded_ice_mask,
+                 resolution):
+        self.xx, self.yy = xx, yy
+        self.initial_bed = initial_bed
+        self.surf, self.velx, self.vely, self.dhdt, self.smb = surf, velx, vely, dhdt, smb
+        self.cond_bed = cond_bed
+        self.data_mask = data_mask
+        self.grounded_ice_mask = grounded_ice_mask
+        self.resolution = resolution
+        self.loss_function_list = []
+        self.sample_loc = None
+        shp = initial_bed.shape
+        if any(a.shape != shp for a in (surf, velx, vely, dhdt, smb, cond_bed, data_mask)):
+            raise Exception("the shape of bed, surf, velx, vely, dhdt, smb, radar_bed, data_mask need to be same")
+        self._ctx = None
+        self._ctx_key = None
+        self._philox_iter = 1        # iteration 0 is the initial state (MCMC.py:1193-1199)
+        self.__init_func__()
+
+    def set_update_region(self, update_in_region, region_mask=[]):
+        self.update_in_region = update_in_region
+        if update_in_region is False or update_in_region == False:  # noqa: E712  (reference accepts 0/False)
+            print("the update blocks is set to be randomly generated for any locations inside the entire map")
+            self.region_mask = np.full(self.xx.shape, 1)
+        else:
+            if np.shape(region_mask) != self.xx.shape:
+                raise ValueError("the region_mask input is invalid. It has to be a 2D numpy array with the shape of the map")
+            print("the update blocks is set to be randomly generated for any locations inside the given region")
+            self.region_mask = region_mask
+        self._ctx = None
+
+    def set_loss_type(self, sigma_mc=-1, massConvInRegion=True):
+        if massConvInRegion:
+            self.mc_region_mask = self.region_mask
+        else:
+            self.mc_region_mask = np.full(self.xx.shape, 1)
+        self.sigma_mc = sigma_mc
+        self._ctx = None
+
+    def set_random_generator(self, rng_seed=None):
+        self.rng_seed_int, self.rng = _seed_to_int(rng_seed, "chain")
+        if isinstance(rng_seed, np.random.Generator):
+            chain.seed = rng_seed        # the reference stores it on the class (MCMC.py:1062)
+
+    def set_sample_points_locations(self, loc):
+        self.sample_loc = loc
+
+    # ---- device context ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _binary(mask, name):
+        m = np.asarray(mask)
+        if not np.isin(m, (0, 1)).all():
+            raise ValueError(f"{name} must contain only 0/1 (the reference mixes `== 1` and truthiness tests, which agree "
+                             "only for binary masks)")
+        return m.astype(np.uint8)
+
+    def _static_args(self):
+        gate = self.region_mask if self.update_in_region else self.grounded_ice_mask
+        gate = self._binary(gate, "region_mask/grounded_ice_mask")
+        mc = self._binary(self.mc_region_mask, "mc_region_mask")
+        centre = np.flatnonzero(self._binary(self.region_mask, "region_mask").ravel() == 1).astype(np.int32) \
+            if self.update_in_region else None
+        if centre is not None and centre.size == 0:
+            raise ValueError("region_mask selects no cell: the reference would loop forever drawing a block centre")
+        weight = self.crf_data_weight if getattr(self, "block_type", "RF") == "CRF_weight" else None
+        return dict(surf=self.surf, velx=self.velx, vely=self.vely, dhdt=self.dhdt, smb=self.smb, gate_mask=gate, mc_mask=mc,
+                    centre_cells=centre, crf_weight=weight, resolution=self.resolution, sigma_mc=self.sigma_mc)
+
+    def _context(self, max_chains=1, RF=None, device=None):
+        key = (max_chains, id(RF), str(device))
+        if self._ctx is None or self._ctx_key != key:
+            H, W = self.xx.shape
+            ctx = Context(H, W, max_chains, device)
+            ctx.set_static(**self._static_args())
+            if RF is not None:
+                ctx.set_field_model(RF.model_name, RF.smoothness, RF.isotropic, RF.range_min_x, RF.range_max_x,
+                                    RF.range_min_y, RF.range_max_y, RF.scale_min, RF.scale_max, RF.nugget_max)
+                ctx.set_blocks(RF.pairs, RF.edge_masks, RF.resolution)
+            self._ctx, self._ctx_key = ctx, key
+        return self._ctx
+
+    def loss(self, massConvResidual, dataDiff):
+        """(total, mc, data) = nansum(res[mc_region_mask==1]^2)/(2 sigma_mc^2), data loss 0 (MCMC.py:1021-1044); K3."""
+        import torch
+        ctx = self._context(1, getattr(self, "_last_rf", None))
+        res = torch.as_tensor(np.ascontiguousarray(massConvResidual, dtype=np.float64), device=ctx.device)[None]
+        out = torch.empty(1, dtype=torch.float64, device=ctx.device)
+        ctx.loss(res.contiguous(), out)
+        loss_mc = float(out.item())
+        return loss_mc + 0, loss_mc, 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# chain_crf                                                                                  reference MCMC.py:1083-1443
+# ------------------------------------------------------------------------------------------------------------------
+class chain_crf(chain):
+    def __init_func__(self):
+        print("before running the chain, please set where the block update will be using the object's function "
+              "set_update_region(update_in_region, region_mask)")
+        print("then please set up the loss function using either set_loss_type or set_loss_func")
+        print("an RandField object also need to be created correctly and passed in set_crf_data_weight(RF) and in run(n_iter, RF)")
+
+    def set_update_type(self, block_type):
+        if block_type == "CRF_rbf":
+            print("The update block is set to conditional random field generated by rbf method (not implemented yet)")
+        elif block_type == "CRF_weight":
+            print("The update block is set to conditional random field generated by calculating weights with logistic function")
+        elif block_type == "RF":
+            print("The update block is set to Random Field")
+        else:
+            raise ValueError("The block_type argument should be one of the following: CRF_weight, CRF_rbf, RF")
+        self.block_type = block_type
+        self._ctx = None
+
+    def set_crf_data_weight(self, RF):
+        self.crf_data_weight = RF.get_crf_weight(self.xx, self.yy, self.data_mask)[0]
+        self._ctx = None
+
+    # ---- the hot loop ------------------------------------------------------------------------------------------
+    def run(self, n_iter, RF, only_save_last_bed=False, info_per_iter=1000, plot=True, progress_bar=True, *,
+            replay=None, resync_every=4096):
+        """Run n_iter-1 Metropolis proposals on the GPU; same return tuple as the reference (MCMC.py:1137, 1434-1443).
+
+        replay: optional sequence of dict(f, idx_x, idx_y, u) — the recorded proposals of a reference run; the chain
+        then replays them through gmc_step_injected and reproduces the reference trajectory bit-for-bit.
+        plot / progress_bar are accepted for signature compatibility (UI is out of scope): a one-line summary is printed
+        every `info_per_iter` iterations when progress_bar is False, like the reference's status line.
+        """
+        if not isinstance(RF, RandField):
+            raise TypeError('The arugment "RF" has to be an object of the class RandField')
+        if not hasattr(self, "rng_seed_int"):
+            self.set_random_generator(None)
+        batch = ChainBatch(self, RF, np.asarray(self.initial_bed, dtype=np.float64)[None],
+                           [philox_key(self.rng_seed_int, RF.rng_seed_int)], iter0=self._philox_iter,
+                           track_resampled=True)
+        self._last_rf = RF
+        H, W = self.xx.shape
+        loss_cache = np.zeros(n_iter)
+        step_cache = np.zeros(n_iter)
+        blocks_cache = np.full((n_iter, 4), np.nan)
+        bed_cache = None if only_save_last_bed else np.zeros((n_iter, H, W))
+        sample_values = sample_ij = None
+        if self.sample_loc is not None:
+            sample_values = np.zeros((self.sample_loc.shape[0], n_iter))
+            sample_ij = np.zeros(self.sample_loc.shape, dtype=np.int64)
+            for k in range(self.sample_loc.shape[0]):
+                si, sj = np.where((self.xx == self.sample_loc[k, 0]) & (self.yy == self.sample_loc[k, 1]))
+                sample_ij[k, :] = [int(si[0]), int(sj[0])]
+            sample_values[:, 0] = np.asarray(self.initial_bed)[sample_ij[:, 0], sample_ij[:, 1]]
+        loss_cache[0] = batch.loss()[0]
+        if bed_cache is not None:
+            bed_cache[0] = self.initial_bed
+
+        per_step = (bed_cache is not None) or (sample_values is not None) or (replay is not None)
+        t0 = time.time()
+        done = 1
+        while done < n_iter:
+            if replay is not None:
+                p = replay[done - 1]
+                acc, loss_now = batch.step_injected([p["f"]], [(p["idx_x"], p["idx_y"])], [p["u"]])
+                loss_cache[done], step_cache[done] = loss_now[0], acc[0]
+                blocks_cache[done] = [p["idx_x"], p["idx_y"], p["f"].shape[0], p["f"].shape[1]]
+                n = 1
+            else:
+                n = 1 if per_step else min(n_iter - done, max(int(info_per_iter), 1) if not progress_bar else n_iter)
+                lc, st, bl = batch.advance(n, resync_every=resync_every)
+                loss_cache[done:done + n], step_cache[done:done + n], blocks_cache[done:done + n] = lc[0], st[0], bl[0]
+            done += n
+            if bed_cache is not None or sample_values is not None:
+                bed_now = batch.beds()[0]
+                if bed_cache is not None:
+                    bed_cache[done - 1] = bed_now
+                if sample_values is not None:
+                    sample_values[:, done - 1] = bed_now[sample_ij[:, 0], sample_ij[:, 1]]
+            if not progress_bar and ((done - 1) % max(int(info_per_iter), 1) == 0 or done == n_iter):
+                el = max(time.time() - t0, 1e-9)
+                print(f"Chain {getattr(self, 'chain_id', 'Unknown')} ({str(getattr(self, 'seed', 'Unknown'))[:6]}): "
+                      f"{100.0 * (done - 1) / max(n_iter - 1, 1):3.0f}% | it/s: {(done - 1) / el:8.2f} | n: {n_iter} | "
+                      f"loss: {loss_cache[done - 1]:.3e} | acc: {np.sum(step_cache) / done:.4f}")
+                sys.stdout.flush()
+        self._philox_iter = batch.iteration
+        bed_c = batch.beds()[0]
+        resampled = batch.resampled_times()[0]
+        loss_data_cache = np.zeros(n_iter)
+        loss_mc_cache = loss_cache.copy()
+        first = bed_c if only_save_last_bed else bed_cache
+        out = (first, loss_mc_cache, loss_data_cache, loss_cache, step_cache, resampled, blocks_cache)
+        batch.close()
+        return out + ((sample_values,) if sample_values is not None else ())
+
+    def run_many(self, n_iter, RF, initial_beds, rng_seeds, device=None, resync_every=4096, track_resampled=True):
+        """Batched form: C independent chains (one per initial bed / seed) stepped concurrently on one GPU.
+
+        Returns a list of the reference's 7-tuples (only_save_last_bed=True form), one per chain — what
+        largeScaleChain_mp collects from its worker processes (largeScaleChain_multiprocessing.py:78-79).
+        """
+        if not isinstance(RF, RandField):
+            raise TypeError('The arugment "RF" has to be an object of the class RandField')
+        beds = np.ascontiguousarray(np.asarray(initial_beds, dtype=np.float64))
+        keys = [philox_key(s, s) for s in rng_seeds]
+        batch = ChainBatch(self, RF, beds, keys, iter0=1, device=device, track_resampled=track_resampled)
+        C = beds.shape[0]
+        loss0 = batch.loss()
+        lc, st, bl = batch.advance(n_iter - 1, resync_every=resync_every)
+        final = batch.beds()
+        res_t = batch.resampled_times() if track_resampled else [np.zeros(beds.shape[1:])] * C
+        out = []
+        for c in range(C):
+            loss = np.concatenate([[loss0[c]], lc[c]])
+            steps = np.concatenate([[0.0], st[c].astype(np.float64)])
+            blocks = np.vstack([np.full((1, 4), np.nan), bl[c].astype(np.float64)])
+            out.append((final[c], loss.copy(), np.zeros(n_iter), loss, steps, res_t[c], blocks))
+        batch.close()
+        return out
+
+
+class ChainBatch:
+    """Device-resident state of C chains sharing one chain_crf configuration: bed[C,H,W], mcres[C,H,W], ssq[C]."""
+
+    def __init__(self, chain_obj, RF, initial_beds, keys, iter0=1, device=None, track_resampled=False):
+        import torch
+        RF._require_spectral()
+        self.torch = torch
+        beds = np.ascontiguousarray(initial_beds, dtype=np.float64)
+        if beds.ndim != 3 or beds.shape[1:] != chain_obj.xx.shape:
+            raise GmcShapeError(f"initial beds have shape {beds.shape}, expected [C,{chain_obj.xx.shape[0]},{chain_obj.xx.shape[1]}]")
+        self.C, self.H, self.W = beds.shape
+        if len(keys) != self.C:
+            raise ValueError("one seed per chain is required")
+        self.chain = chain_obj
+        self.ctx = chain_obj._context(self.C, RF, device)
+        dev = self.ctx.device
+        self.dev = dev
+        self.gate = np.asarray(chain_obj.region_mask if chain_obj.update_in_region else chain_obj.grounded_ice_mask)
+        self.bed = torch.as_tensor(beds).to(dev, non_blocking=False).contiguous()
+        self.mcres = torch.empty_like(self.bed)
+        self.ssq = torch.empty(self.C, dtype=torch.float64, device=dev)
+        self._loss = torch.empty(self.C, dtype=torch.float64, device=dev)
+        self.seeds = keys_tensor(keys, dev)
+        self.resampled = torch.zeros((self.C, self.H, self.W), dtype=torch.int32, device=dev) if track_resampled else None
+        self.iteration = int(iter0)
+        self.ctx.residual_loss(self.bed, self.mcres, self._loss, self.ssq)
+
+    def close(self):
+        self.bed = self.mcres = self.resampled = None
+
+    def loss(self):
+        return (self.ssq / (2 * self.chain.sigma_mc ** 2)).cpu().numpy()
+
+    def beds(self):
+        return self.bed.cpu().numpy()
+
+    def residuals(self):
+        return self.mcres.cpu().numpy()
+
+    def resampled_times(self):
+        """float64 [C,H,W]: accepted-block coverage counts times the mask value (MCMC.py:1349-1352)."""
+        if self.resampled is None:
+            raise GmcError("ChainBatch was created with track_resampled=False")
+        return self.resampled.cpu().numpy().astype(np.float64) * self.gate[None].astype(np.float64)
+
+    def advance(self, n_steps, resync_every=4096, want_caches=True):
+        """n_steps fused free-running iterations (kernel K1+K4).  Returns (loss[C,n], accepted[C,n], blocks[C,n,4])."""
+        torch = self.torch
+        lc = st = bl = None
+        if want_caches:
+            lc = torch.empty((self.C, n_steps), dtype=torch.float64, device=self.dev)
+            st = torch.empty((self.C, n_steps), dtype=torch.uint8, device=self.dev)
+            bl = torch.empty((self.C, n_steps, 4), dtype=torch.int32, device=self.dev)
+        self.ctx.run(self.bed, self.mcres, self.ssq, self.seeds, self.iteration, n_steps, lc, st, bl, 0, self.resampled,
+                     resync_every)
+        self.iteration += n_steps
+        if not want_caches:
+            return None
+        return lc.cpu().numpy(), st.cpu().numpy(), bl.cpu().numpy()
+
+    def step_injected(self, fields, centres, us):
+        """One step per chain with injected proposals.  Returns (accepted[C] bool, loss[C])."""
+        torch = self.torch
+        hmax = max(f.shape[0] for f in fields)
+        wmax = max(f.shape[1] for f in fields)
+        stride = hmax * wmax
+        fbuf = np.zeros((self.C, stride))
+        hw = np.zeros((self.C, 2), dtype=np.int32)
+        for c, f in enumerate(fields):
+            fbuf[c, :f.size] = np.ascontiguousarray(f, dtype=np.float64).ravel()
+            hw[c] = f.shape
+        dev = self.dev
+        acc = torch.empty(self.C, dtype=torch.uint8, device=dev)
+        loss = torch.empty(self.C, dtype=torch.float64, device=dev)
+        self.ctx.step_injected(self.bed, self.mcres, self.ssq, torch.as_tensor(fbuf).to(dev), torch.as_tensor(hw).to(dev),
+                               torch.as_tensor(np.asarray(centres, dtype=np.int32).reshape(self.C, 2)).to(dev),
+                               torch.as_tensor(np.asarray(us, dtype=np.float64)).to(dev), hmax, wmax, acc, loss, None,
+                               self.resampled)
+        self.iteration += 1
+        return acc.cpu().numpy().astype(bool), loss.cpu().numpy()

@@ -1,0 +1,15 @@
+"""mcmc_gpu_b200 — B200-native (sm_100a) many-chain MCMC step for gstatsMCMC's large-scale chain.
+
+`from mcmc_gpu_b200 import MCMC, Topography` mirrors `from gstatsMCMC import MCMC, Topography` for the hot path.
+Importing the package does not need a GPU; any computation does (no CPU fallback).
+"""
+from . import synthetic  # noqa: F401
+
+__all__ = ["MCMC", "Topography", "synthetic", "drivers"]
+
+
+def __getattr__(name):
+    if name in ("MCMC", "Topography", "drivers", "_lib"):
+        import importlib
+        return importlib.import_module(f"{__name__}.{name}")
+    raise AttributeError(name)

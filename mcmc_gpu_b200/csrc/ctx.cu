@@ -1,0 +1,319 @@
+// ctx.cu — context lifetime and the setup calls of libgmc (host code only; no kernels here).
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gmc_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* gmc_last_error(void) { return g_err; }
+extern "C" int gmc_version(void) { return 100; }
+
+int gmc_step_configure(gmc_ctx* ctx);   // step.cu: sizes dynamic smem for the current block table
+
+extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chains) {
+    if (!out) GMC_FAIL(GMC_EINVAL, "gmc_create: out is NULL");
+    *out = nullptr;
+    if (H < 2 || W < 2) GMC_FAIL(GMC_ESHAPE, "gmc_create: grid %dx%d too small (np.gradient needs >= 2 per axis)", H, W);
+    if (max_chains < 1) GMC_FAIL(GMC_EINVAL, "gmc_create: max_chains must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        GMC_FAIL(GMC_ECUDA, "gmc_create: no CUDA device available (%s); libgmc has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= ndev) GMC_FAIL(GMC_EINVAL, "gmc_create: device %d out of range [0,%d)", device, ndev);
+    GMC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GMC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        GMC_FAIL(GMC_ECUDA, "gmc_create: device %d is sm_%d%d; libgmc is built for sm_100a (B200) only", device, prop.major,
+                 prop.minor);
+    gmc_ctx* c = new gmc_ctx();
+    memset(&c->dev, 0, sizeof(c->dev));
+    c->device = device;
+    c->H = H;
+    c->W = W;
+    c->max_chains = max_chains;
+    c->sm_count = prop.multiProcessorCount;
+    c->have_static = c->have_model = c->have_blocks = false;
+    c->d_static = nullptr;
+    c->d_flags = nullptr;
+    c->d_centre = nullptr;
+    c->d_partials = nullptr;
+    c->d_pairs = nullptr;
+    c->d_plans = nullptr;
+    c->d_twiddle = nullptr;
+    c->d_perm = c->d_pos = nullptr;
+    c->d_ksq = nullptr;
+    c->d_edge_masks = nullptr;
+    c->max_h = c->max_w = 0;
+    c->step_smem_bytes = 0;
+    c->step_ctas_per_sm = 0;
+    c->launches = 0;
+    c->dev.H = H;
+    c->dev.W = W;
+    // loss partials: one per (chain, row-tile); sized for the residual kernel's tiling (residual.cu)
+    c->n_tiles = 0;
+    *out = c;
+    return GMC_OK;
+}
+
+extern "C" int gmc_destroy(gmc_ctx* c) {
+    if (!c) return GMC_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_static);
+    cudaFree(c->d_flags);
+    cudaFree(c->d_centre);
+    cudaFree(c->d_partials);
+    cudaFree(c->d_pairs);
+    cudaFree(c->d_plans);
+    cudaFree(c->d_twiddle);
+    cudaFree(c->d_perm);
+    cudaFree(c->d_pos);
+    cudaFree(c->d_ksq);
+    cudaFree(c->d_edge_masks);
+    delete c;
+    return GMC_OK;
+}
+
+extern "C" int gmc_set_static(gmc_ctx* c, const double* surf, const double* velx, const double* vely, const double* dhdt,
+                              const double* smb, const uint8_t* gate_mask, const uint8_t* mc_mask,
+                              const int32_t* centre_cells, int64_t n_centre_cells, const double* crf_weight,
+                              double resolution, double sigma_mc) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_set_static: ctx is NULL");
+    if (!surf || !velx || !vely || !dhdt || !smb || !gate_mask || !mc_mask)
+        GMC_FAIL(GMC_EINVAL, "gmc_set_static: NULL field or mask pointer");
+    if (!(resolution > 0.0)) GMC_FAIL(GMC_EINVAL, "gmc_set_static: resolution must be > 0");
+    if (n_centre_cells < 0 || (n_centre_cells > 0 && !centre_cells))
+        GMC_FAIL(GMC_EINVAL, "gmc_set_static: centre_cells/n_centre_cells inconsistent");
+    GMC_CUDA(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->H * c->W;
+    if (!c->d_static) GMC_CUDA(cudaMalloc(&c->d_static, 6 * n * sizeof(double)));
+    if (!c->d_flags) GMC_CUDA(cudaMalloc(&c->d_flags, n));
+    const double* src[6] = {surf, velx, vely, dhdt, smb, crf_weight};
+    for (int k = 0; k < 6; ++k)
+        if (src[k]) GMC_CUDA(cudaMemcpy(c->d_static + k * n, src[k], n * sizeof(double), cudaMemcpyDefault));
+    // pack the two masks into one flag byte per cell (host side; setup is not on the hot path)
+    std::vector<uint8_t> g(n), m(n), fl(n);
+    GMC_CUDA(cudaMemcpy(g.data(), gate_mask, n, cudaMemcpyDefault));
+    GMC_CUDA(cudaMemcpy(m.data(), mc_mask, n, cudaMemcpyDefault));
+    for (size_t i = 0; i < n; ++i) {
+        if (g[i] > 1 || m[i] > 1) GMC_FAIL(GMC_EINVAL, "gmc_set_static: masks must hold 0/1 (cell %zu has %d/%d)", i, g[i], m[i]);
+        fl[i] = (uint8_t)((g[i] ? FLAG_GATE : 0) | (m[i] ? FLAG_MC : 0));
+    }
+    GMC_CUDA(cudaMemcpy(c->d_flags, fl.data(), n, cudaMemcpyHostToDevice));
+    cudaFree(c->d_centre);
+    c->d_centre = nullptr;
+    if (n_centre_cells > 0) {
+        std::vector<int32_t> cc((size_t)n_centre_cells);
+        GMC_CUDA(cudaMemcpy(cc.data(), centre_cells, cc.size() * sizeof(int32_t), cudaMemcpyDefault));
+        for (int32_t v : cc)
+            if (v < 0 || (size_t)v >= n) GMC_FAIL(GMC_EINVAL, "gmc_set_static: centre cell index %d outside the grid", v);
+        GMC_CUDA(cudaMalloc(&c->d_centre, cc.size() * sizeof(int32_t)));
+        GMC_CUDA(cudaMemcpy(c->d_centre, cc.data(), cc.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    GmcDev& d = c->dev;
+    d.surf = c->d_static;
+    d.velx = c->d_static + n;
+    d.vely = c->d_static + 2 * n;
+    d.dhdt = c->d_static + 3 * n;
+    d.smb = c->d_static + 4 * n;
+    d.crf_weight = crf_weight ? c->d_static + 5 * n : nullptr;
+    d.flags = c->d_flags;
+    d.centre_cells = c->d_centre;
+    d.n_centre_cells = n_centre_cells;
+    d.res = resolution;
+    d.two_res = 2.0 * resolution;              // np.gradient: 2. * ax_dx
+    d.two_sigma2 = 2 * (sigma_mc * sigma_mc);  // MCMC.py:1041: 2*self.sigma_mc**2
+    c->have_static = true;
+    return GMC_OK;
+}
+
+extern "C" int gmc_set_field_model(gmc_ctx* c, int model, double smoothness, int isotropic, double range_min_x,
+                                   double range_max_x, double range_min_y, double range_max_y, double scale_min,
+                                   double scale_max, double nugget_max) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_set_field_model: ctx is NULL");
+    if (model != GMC_GAUSSIAN && model != GMC_EXPONENTIAL && model != GMC_MATERN)
+        GMC_FAIL(GMC_EINVAL, "gmc_set_field_model: model must be Gaussian(0), Exponential(1) or Matern(2)");
+    if (nugget_max < 0.0) GMC_FAIL(GMC_EINVAL, "gmc_set_field_model: nugget_max must be >= 0");
+    GmcFieldModel& f = c->dev.fm;
+    f.model = model;
+    f.isotropic = isotropic ? 1 : 0;
+    // MCMC.py:232: nu = RF.smoothness or 1.0
+    f.smoothness = (model == GMC_MATERN) ? ((smoothness == 0.0 || smoothness != smoothness) ? 1.0 : smoothness) : 1.0;
+    f.range_min_x = range_min_x;
+    f.range_max_x = range_max_x;
+    f.range_min_y = range_min_y;
+    f.range_max_y = range_max_y;
+    f.scale_min = scale_min;
+    f.scale_max = scale_max;
+    f.nugget_max = nugget_max;
+    const double nu = f.smoothness;
+    f.matern_num = 4 * M_PI * tgamma(nu + 1) * pow(2 * nu, nu);   // MCMC.py:236 numerator
+    f.matern_gamma = tgamma(nu);
+    c->have_model = true;
+    return GMC_OK;
+}
+
+// ---- FFT plans -----------------------------------------------------------------------------------------------
+static bool factorize(int n, GmcFftPlan& p) {
+    p.n = n;
+    p.n_factors = 0;
+    int m = n, twos = 0;
+    while (m % 2 == 0) {
+        m /= 2;
+        ++twos;
+    }
+    auto push = [&](int r) {
+        if (p.n_factors >= GMC_MAX_FACTORS) return false;
+        p.radix[p.n_factors++] = r;
+        return true;
+    };
+    for (; twos >= 3; twos -= 3)
+        if (!push(8)) return false;
+    if (twos == 2 && !push(4)) return false;
+    if (twos == 1 && !push(2)) return false;
+    for (int r = 3; r < GMC_MAX_RADIX; r += 2) {   // 3, 5, 7, 11, 13 have unrolled stages; larger primes a generic one
+        while (m % r == 0) {
+            if (!push(r)) return false;
+            m /= r;
+        }
+    }
+    return m == 1;
+}
+
+extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, const int32_t* pair_h,
+                              const double* edge_masks, const int64_t* offsets, double field_resolution) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_set_blocks: ctx is NULL");
+    if (n_pairs < 1 || !pair_w || !pair_h || !edge_masks || !offsets)
+        GMC_FAIL(GMC_EINVAL, "gmc_set_blocks: empty block table or NULL pointer");
+    if (!(field_resolution > 0.0)) GMC_FAIL(GMC_EINVAL, "gmc_set_blocks: field_resolution must be > 0");
+    GMC_CUDA(cudaSetDevice(c->device));
+    std::vector<GmcPair> pairs(n_pairs);
+    std::vector<GmcFftPlan> plans;
+    std::vector<double2> tw;
+    std::vector<int16_t> perm, pos;
+    std::vector<double> ksq;
+    auto plan_for = [&](int n) -> int {
+        for (size_t i = 0; i < plans.size(); ++i)
+            if (plans[i].n == n) return (int)i;
+        GmcFftPlan p;
+        if (!factorize(n, p)) return -1;
+        p.tw_off = (int)tw.size();
+        for (int k = 0; k < n; ++k) {
+            // exp(+2 pi i k/n) with the argument reduced exactly before the libm call
+            const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+            tw.push_back(make_double2((double)cosl(a), (double)sinl(a)));
+        }
+        std::vector<int> cur(1, 0);
+        for (int s = 0; s < p.n_factors; ++s) {
+            const int r = p.radix[s];
+            std::vector<int> nxt;
+            nxt.reserve(cur.size() * r);
+            for (int q = 0; q < r; ++q)
+                for (int v : cur) nxt.push_back(q + r * v);
+            cur.swap(nxt);
+        }
+        p.perm_off = (int)perm.size();
+        p.pos_off = (int)pos.size();
+        std::vector<int16_t> inv(n);
+        for (int i = 0; i < n; ++i) {
+            perm.push_back((int16_t)cur[i]);
+            inv[cur[i]] = (int16_t)i;
+        }
+        pos.insert(pos.end(), inv.begin(), inv.end());
+        p.ksq_off = (int)ksq.size();
+        const double val = 1.0 / (n * field_resolution);   // np.fft.fftfreq: val = 1.0/(n*d); results * val
+        for (int i = 0; i <= n / 2; ++i) {
+            const double kk = (double)i * val * 2 * M_PI;  // MCMC.py:221: fftfreq(...) * 2 * np.pi
+            ksq.push_back(kk * kk);
+        }
+        plans.push_back(p);
+        return (int)plans.size() - 1;
+    };
+    int64_t total = 0;
+    int mh = 0, mw = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+        const int w = pair_w[i], h = pair_h[i];
+        if (w < 2 || h < 2 || (w & 1) || (h & 1))
+            GMC_FAIL(GMC_EINVAL, "gmc_set_blocks: pair %d is %dx%d; block edges must be even and >= 2 (MCMC.py:579)", i, h, w);
+        if (h > c->H || w > c->W)
+            GMC_FAIL(GMC_ESHAPE, "gmc_set_blocks: pair %d (%dx%d) is larger than the %dx%d grid", i, h, w, c->H, c->W);
+        if (w > 32767 || h > 32767) GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: block edge > 32767");
+        pairs[i].h = h;
+        pairs[i].w = w;
+        pairs[i].plan_h = plan_for(h);
+        pairs[i].plan_w = plan_for(w);
+        if (pairs[i].plan_h < 0 || pairs[i].plan_w < 0)
+            GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: pair %d (%dx%d) has a prime factor >= %d", i, h, w, GMC_MAX_RADIX);
+        pairs[i].mask_off = offsets[i];
+        total = std::max<int64_t>(total, offsets[i] + (int64_t)h * w);
+        mh = std::max(mh, h);
+        mw = std::max(mw, w);
+    }
+    cudaFree(c->d_pairs);
+    cudaFree(c->d_plans);
+    cudaFree(c->d_twiddle);
+    cudaFree(c->d_perm);
+    cudaFree(c->d_pos);
+    cudaFree(c->d_ksq);
+    cudaFree(c->d_edge_masks);
+    c->d_pairs = nullptr;
+    c->d_plans = nullptr;
+    c->d_twiddle = nullptr;
+    c->d_perm = c->d_pos = nullptr;
+    c->d_ksq = nullptr;
+    c->d_edge_masks = nullptr;
+    c->have_blocks = false;
+#define UPLOAD(dst, vec)                                                                          \
+    GMC_CUDA(cudaMalloc(&(dst), (vec).size() * sizeof((vec)[0])));                                 \
+    GMC_CUDA(cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
+    UPLOAD(c->d_pairs, pairs);
+    UPLOAD(c->d_plans, plans);
+    UPLOAD(c->d_twiddle, tw);
+    UPLOAD(c->d_perm, perm);
+    UPLOAD(c->d_pos, pos);
+    UPLOAD(c->d_ksq, ksq);
+#undef UPLOAD
+    GMC_CUDA(cudaMalloc(&c->d_edge_masks, (size_t)total * sizeof(double)));
+    GMC_CUDA(cudaMemcpy(c->d_edge_masks, edge_masks, (size_t)total * sizeof(double), cudaMemcpyDefault));
+    c->h_pairs = pairs;
+    c->h_plans = plans;
+    c->max_h = mh;
+    c->max_w = mw;
+    GmcDev& d = c->dev;
+    d.n_pairs = n_pairs;
+    d.pairs = c->d_pairs;
+    d.plans = c->d_plans;
+    d.twiddle = c->d_twiddle;
+    d.perm = c->d_perm;
+    d.pos = c->d_pos;
+    d.ksq = c->d_ksq;
+    d.edge_masks = c->d_edge_masks;
+    const int rc = gmc_step_configure(c);
+    if (rc != GMC_OK) return rc;
+    c->have_blocks = true;
+    return GMC_OK;
+}
+
+extern "C" int64_t gmc_launch_count(const gmc_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int gmc_step_kernel_info(const gmc_ctx* c, int* smem_bytes, int* threads, int* ctas_per_sm) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_step_kernel_info: ctx is NULL");
+    if (!c->have_blocks) GMC_FAIL(GMC_ESTATE, "gmc_step_kernel_info: call gmc_set_blocks first");
+    if (smem_bytes) *smem_bytes = c->step_smem_bytes;
+    if (threads) *threads = GMC_STEP_THREADS;
+    if (ctas_per_sm) *ctas_per_sm = c->step_ctas_per_sm;
+    return GMC_OK;
+}

@@ -1,0 +1,90 @@
+// ensemble.cu — K5: per-GPU partial moments of the chain ensemble and the one collective on the path.
+//
+// The reference never forms cross-chain statistics on the fly (visualization.ipynb loads per-chain files); here each
+// GPU reduces its own chains to sum (bed - ref) and sum (bed - ref)^2 per cell (HBM-bound: reads C*H*W*8 bytes once)
+// and a single fp64 SUM all-reduce of 2*H*W+1 values combines the GPUs.
+#include <dlfcn.h>
+
+#include "common.cuh"
+
+// each thread owns two adjacent cells and walks the chain axis: coalesced 16 B loads, fixed summation order
+__global__ void __launch_bounds__(256)
+    moments_kernel(const double* __restrict__ bed, const double* __restrict__ ref, double* __restrict__ sum_out,
+                   double* __restrict__ sumsq_out, int64_t plane, int C) {
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (k >= plane) return;
+    if (k + 1 < plane && (plane & 1) == 0) {
+        const double2 r = *reinterpret_cast<const double2*>(ref + k);
+        double s0 = 0, s1 = 0, q0 = 0, q1 = 0;
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            const double2 b = __ldcs(reinterpret_cast<const double2*>(bed + (int64_t)c * plane + k));
+            const double d0 = b.x - r.x, d1 = b.y - r.y;
+            s0 += d0;
+            s1 += d1;
+            q0 += d0 * d0;
+            q1 += d1 * d1;
+        }
+        *reinterpret_cast<double2*>(sum_out + k) = make_double2(s0, s1);
+        *reinterpret_cast<double2*>(sumsq_out + k) = make_double2(q0, q1);
+    } else {
+        for (int64_t kk = k; kk < plane && kk < k + 2; ++kk) {
+            const double r = ref[kk];
+            double s = 0, q = 0;
+            for (int c = 0; c < C; ++c) {
+                const double dd = bed[(int64_t)c * plane + kk] - r;
+                s += dd;
+                q += dd * dd;
+            }
+            sum_out[kk] = s;
+            sumsq_out[kk] = q;
+        }
+    }
+}
+
+extern "C" int gmc_ensemble_moments(gmc_ctx* c, const double* bed, const double* ref_bed, double* sum_out,
+                                    double* sumsq_out, int C, void* stream) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_ensemble_moments: ctx is NULL");
+    if (!bed || !ref_bed || !sum_out || !sumsq_out) GMC_FAIL(GMC_EINVAL, "gmc_ensemble_moments: NULL argument");
+    if (C < 1 || C > c->max_chains) GMC_FAIL(GMC_ESHAPE, "gmc_ensemble_moments: C=%d outside [1,%d]", C, c->max_chains);
+    GMC_CUDA(cudaSetDevice(c->device));
+    const int64_t plane = (int64_t)c->H * c->W;
+    const int64_t threads = (plane + 1) / 2;
+    moments_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bed, ref_bed, sum_out, sumsq_out, plane, C);
+    c->launches++;
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+// ---- NCCL, resolved at run time so libgmc.so carries no link-time dependency on a particular libnccl -----------
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*nccl_errstr_fn)(int);
+typedef int (*nccl_group_fn)(void);
+
+static void* nccl_sym(const char* name) {
+    void* s = dlsym(RTLD_DEFAULT, name);
+    if (s) return s;
+    static void* handle = nullptr;
+    if (!handle) handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    return handle ? dlsym(handle, name) : nullptr;
+}
+
+extern "C" int gmc_allreduce_moments(gmc_ctx* c, void* comm, double* sum, double* sumsq, double* count, void* stream) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_allreduce_moments: ctx is NULL");
+    if (!comm || !sum || !sumsq || !count) GMC_FAIL(GMC_EINVAL, "gmc_allreduce_moments: NULL argument");
+    nccl_allreduce_fn ar = (nccl_allreduce_fn)nccl_sym("ncclAllReduce");
+    nccl_errstr_fn es = (nccl_errstr_fn)nccl_sym("ncclGetErrorString");
+    nccl_group_fn gs = (nccl_group_fn)nccl_sym("ncclGroupStart");
+    nccl_group_fn ge = (nccl_group_fn)nccl_sym("ncclGroupEnd");
+    if (!ar || !es || !gs || !ge) GMC_FAIL(GMC_ENCCL, "gmc_allreduce_moments: libnccl.so.2 not loadable (%s)", dlerror());
+    GMC_CUDA(cudaSetDevice(c->device));
+    const size_t plane = (size_t)c->H * c->W;
+    const int kFloat64 = 8, kSum = 0;   // ncclFloat64, ncclSum (nccl.h)
+    int rc = gs();
+    if (!rc) rc = ar(sum, sum, plane, kFloat64, kSum, comm, (cudaStream_t)stream);
+    if (!rc) rc = ar(sumsq, sumsq, plane, kFloat64, kSum, comm, (cudaStream_t)stream);
+    if (!rc) rc = ar(count, count, 1, kFloat64, kSum, comm, (cudaStream_t)stream);
+    const int rc2 = ge();
+    if (rc || rc2) GMC_FAIL(GMC_ENCCL, "gmc_allreduce_moments: NCCL error: %s", es(rc ? rc : rc2));
+    return GMC_OK;
+}

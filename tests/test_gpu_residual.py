@@ -1,0 +1,104 @@
+"""K2/K3 parity: batched residual and masked loss vs the oracle (bit-exact residual, loss <= 1e-12 rel)."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import residual_case_inputs
+from gpu_helpers import same_values
+from oracle import crf_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rand_inputs(H, W, seed, nan_frac=0.0):
+    g = np.random.default_rng(seed)
+    surf = 1500.0 + 300.0 * g.standard_normal((H, W))
+    d = dict(surf=surf, velx=200.0 * g.standard_normal((H, W)), vely=150.0 * g.standard_normal((H, W)),
+             dhdt=g.standard_normal((H, W)), smb=g.standard_normal((H, W)))
+    if nan_frac:
+        d["velx"][g.random((H, W)) < nan_frac] = np.nan
+    return d, g
+
+
+def test_topography_api_matches_reference_golden():
+    from mcmc_gpu_b200 import Topography
+    ri = residual_case_inputs()
+    gold = np.load(os.path.join(GOLD, "residual_loss.npz"))
+    res = Topography.get_mass_conservation_residual(ri["bed"], ri["surf"], ri["velx"], ri["vely"], ri["dhdt"], ri["smb"],
+                                                    ri["resolution"])
+    assert same_values(res, gold["residual"])
+
+
+def test_topography_tensor_api():
+    import torch
+    from mcmc_gpu_b200 import Topography
+    ri = residual_case_inputs()
+    t = {k: torch.as_tensor(ri[k]).cuda() for k in ("bed", "surf", "velx", "vely", "dhdt", "smb")}
+    res = Topography.get_mass_conservation_residual_tensor(t["bed"], t["surf"], t["velx"], t["vely"], t["dhdt"], t["smb"],
+                                                           torch.tensor(ri["resolution"]))
+    assert res.is_cuda and res.dtype == torch.float64
+    gold = np.load(os.path.join(GOLD, "residual_loss.npz"))
+    assert same_values(res.cpu().numpy(), gold["residual"])
+
+
+@pytest.mark.parametrize("H,W,C", [(2, 2, 1), (2, 9, 3), (33, 2, 2), (37, 53, 4), (64, 128, 2), (200, 200, 3), (131, 257, 5)])
+def test_batched_residual_and_loss(H, W, C):
+    import torch
+    from mcmc_gpu_b200._lib import Context
+    st, g = _rand_inputs(H, W, 7 + H * W, nan_frac=0.01 if H * W > 100 else 0.0)
+    beds = st["surf"][None] - 800.0 + 100.0 * g.standard_normal((C, H, W))
+    if H * W > 100:
+        beds[0, H // 2, W // 3] = np.nan
+    mask = (g.random((H, W)) < 0.6).astype(np.uint8)
+    sigma, res_m = 3.5, 250.0
+    ctx = Context(H, W, C)
+    ctx.set_static(st["surf"], st["velx"], st["vely"], st["dhdt"], st["smb"], np.ones((H, W)), mask, None, None, res_m, sigma)
+    bed_d = torch.as_tensor(beds).cuda()
+    res_d = torch.empty_like(bed_d)
+    loss_d = torch.empty(C, dtype=torch.float64, device="cuda")
+    ssq_d = torch.empty_like(loss_d)
+    ctx.residual(bed_d, res_d)
+    res = res_d.cpu().numpy()
+    ctx.residual_loss(bed_d, None, loss_d, ssq_d)
+    loss_fused = loss_d.cpu().numpy()
+    ctx.loss(res_d, loss_d)
+    loss_sep = loss_d.cpu().numpy()
+    for c in range(C):
+        ref = O.mass_conservation_residual(beds[c], st["surf"], st["velx"], st["vely"], st["dhdt"], st["smb"], res_m)
+        assert same_values(res[c], ref), f"chain {c}"
+        ref_loss = O.masked_loss(ref, mask, sigma)[0]
+        tol = 1e-12 * max(abs(ref_loss), 1e-300)
+        assert abs(loss_fused[c] - ref_loss) <= tol and abs(loss_sep[c] - ref_loss) <= tol
+    assert np.allclose(ssq_d.cpu().numpy() / (2 * sigma ** 2), loss_fused, rtol=1e-15)
+
+
+def test_chain_loss_method_matches_golden():
+    from gpu_helpers import quiet
+    from mcmc_gpu_b200 import MCMC
+    ri = residual_case_inputs()
+    gold = np.load(os.path.join(GOLD, "residual_loss.npz"))
+    ch = quiet(MCMC.chain_crf, ri["xx"], ri["yy"], ri["bed"], ri["surf"], ri["velx"], ri["vely"], ri["dhdt"], ri["smb"],
+               ri["bed"], ri["mask"], ri["mask"], ri["resolution"])
+    quiet(ch.set_update_region, True, ri["mask"])
+    ch.set_loss_type(sigma_mc=ri["sigma_mc"], massConvInRegion=True)
+    total, mc, data = ch.loss(gold["residual"], 0)
+    assert data == 0 and total == mc
+    assert abs(total - gold["loss"][0]) <= 1e-12 * gold["loss"][0]
+
+
+def test_errors_are_loud():
+    from mcmc_gpu_b200._lib import Context, GmcError, GmcShapeError
+    import torch
+    ctx = Context(8, 8, 2)
+    bed = torch.zeros((2, 8, 8), dtype=torch.float64, device="cuda")
+    with pytest.raises(GmcError):                       # set_static not called
+        ctx.residual(bed, torch.empty_like(bed))
+    z = np.zeros((8, 8))
+    ctx.set_static(z, z, z, z, z, np.ones((8, 8)), np.ones((8, 8)), None, None, 1.0, 1.0)
+    with pytest.raises(GmcShapeError):                  # more chains than the context holds
+        big = torch.zeros((3, 8, 8), dtype=torch.float64, device="cuda")
+        ctx.residual(big, torch.empty_like(big))
+    with pytest.raises(GmcShapeError):
+        Context(1, 8, 1)
