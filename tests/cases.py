@@ -41,9 +41,11 @@ def build_case_grids(case: dict) -> dict:
     return g
 
 
+# Ranges are kept within a few cells of the block size: for a Gaussian spectrum with range >> block the reference's own
+# output is rounding noise of the FFT around a cancelled DC term (ill-conditioned by ~1e9), so no two FFTs agree to 1e-9.
 FIELD_CASES = {
     "matern_iso": dict(rf_kw=MATERN, seed=101, res=500.0, shapes=[(50, 56), (64, 64), (72, 80), (80, 50)]),
-    "gauss_aniso_nug": dict(rf_kw=dict(range_min_x=5e3, range_max_x=20e3, range_min_y=8e3, range_max_y=30e3,
+    "gauss_aniso_nug": dict(rf_kw=dict(range_min_x=1e3, range_max_x=3e3, range_min_y=1.5e3, range_max_y=4e3,
                                        scale_min=10.0, scale_max=30.0, nugget_max=2.5, model_name="Gaussian",
                                        isotropic=False, smoothness=None), seed=102, res=250.0,
                             shapes=[(20, 24), (30, 18), (58, 22)]),
