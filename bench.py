@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py — chain-steps/s of the many-chain large-scale MCMC step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A bench "step" advances every chain by --iters Metropolis iterations (one fused kernel launch per GPU).  Workload at
+N=1 is BASELINE.json configs[1]: 256 chains on the synthetic 500x500 grid (SURVEY.md §8d recipe); at N>1 every GPU
+holds the same number of chains (weak scaling, no data-path collective; the ensemble-moments all-reduce runs once after
+the timed region).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+METRIC = "chain-steps/sec (chains x iters), large-scale chain"
+UNIT = "chain-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=256, help="chains per GPU")
+    ap.add_argument("--grid", type=int, default=500)
+    ap.add_argument("--iters", type=int, default=1000, help="Metropolis iterations per chain per bench step")
+    ap.add_argument("--cpu-iters", type=int, default=0, help="iterations per chain of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"large-scale chain (random-field proposal + mass-conservation loss), {a.chains} chains/GPU, synthetic {a.grid}x{a.grid} grid"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the numpy oracle port of the reference's per-chain loop, one process per core (the reference's
+# largeScaleChain_mp runs one chain per mp.Pool worker, largeScaleChain_multiprocessing.py:78-79)
+# ---------------------------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(grid):
+    from mcmc_gpu_b200 import synthetic as syn
+    from oracle import crf_oracle as O
+    os.environ["OMP_NUM_THREADS"] = "1"
+    g = syn.make_grids(grid, grid)
+    cs, fp = O.setup_from_grids(g, sigma_mc=syn.SIGMA_MC, logistic=syn.LOGISTIC, max_dist=syn.MAX_DIST, blocks=syn.BLOCKS)
+    _CPU.update(g=g, cs=cs, fp=fp, O=O)
+
+
+def _cpu_chain(args):
+    seed, n_iter = args
+    O, g = _CPU["O"], _CPU["g"]
+    out = O.run_chain(_CPU["cs"], _CPU["fp"], g["bed0"], n_iter, np.random.default_rng(seed), np.random.default_rng(seed))
+    return float(out["steps"].mean())
+
+
+def cpu_arm(grid, n_iter, steps, warmup, cores=None):
+    """Returns (chain-steps/s, cores, seconds per step).  Each step = `cores` chains x n_iter iterations."""
+    import multiprocessing as mp
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")       # the parent may hold a CUDA context: never fork it
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(grid,)) as pool:
+        pool.map(_cpu_chain, [(1, 3)] * cores)               # import + setup outside the timed region
+        for w in range(warmup):
+            pool.map(_cpu_chain, [(100 + c, max(n_iter // 10, 3)) for c in range(cores)])
+        t0 = time.perf_counter()
+        for s in range(steps):
+            pool.map(_cpu_chain, [(1000 * (s + 1) + c, n_iter) for c in range(cores)])
+        dt = time.perf_counter() - t0
+    return cores * (n_iter - 1) * steps / dt, cores, dt / steps
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_iter = a.cpu_iters or (400 if a.grid <= 500 else 60)
+    val, cores, sps = cpu_arm(a.grid, n_iter, max(a.steps, 1), a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "grid": [a.grid, a.grid]},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{cores} chains x {n_iter} iterations per step, numpy port of chain_crf.run (oracle/crf_oracle.py), one process per core"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in ln.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def gpu_main(a):
+    import torch
+    import torch.distributed as dist
+    import contextlib
+    import io
+    from mcmc_gpu_b200 import MCMC, synthetic as syn
+
+    def quiet(fn, *args, **kw):
+        with contextlib.redirect_stdout(io.StringIO()):
+            return fn(*args, **kw)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    # ---- workload: tutorial configuration on the synthetic grid, through the public API -------------------------
+    H = W = a.grid
+    C = a.chains
+    g = syn.make_grids(H, W)
+    kw = syn.RF_KW
+    rf = quiet(MCMC.RandField, kw["range_min_x"], kw["range_max_x"], kw["range_min_y"], kw["range_max_y"], kw["scale_min"],
+               kw["scale_max"], kw["nugget_max"], kw["model_name"], kw["isotropic"], smoothness=kw["smoothness"], rng_seed=0)
+    rf.set_block_sizes(*syn.BLOCKS)
+    rf.set_weight_param(*syn.LOGISTIC, syn.MAX_DIST, g["resolution"])
+    rf.set_generation_method(True)
+    ch = quiet(MCMC.chain_crf, g["xx"], g["yy"], g["bed0"], g["surf"], g["velx"], g["vely"], g["dhdt"], g["smb"], g["cond_bed"],
+               g["data_mask"], g["grounded_ice_mask"], g["resolution"])
+    quiet(ch.set_update_region, True, g["highvel_mask"])
+    ch.set_loss_type(sigma_mc=syn.SIGMA_MC, massConvInRegion=True)
+    quiet(ch.set_update_type, "CRF_weight")
+    ch.set_crf_data_weight(rf)
+    seeds = [1000 + rank * C + c for c in range(C)]                 # global chain id -> seed: invariant to GPU count
+    host_beds = torch.empty((C, H, W), dtype=torch.float64).pin_memory()
+    host_beds.copy_(torch.as_tensor(syn.chain_initial_beds(g["bed0"], C)))
+    n_it = a.iters
+    out = {"bed": torch.empty((C, H, W), dtype=torch.float64).pin_memory(),
+           "loss": torch.empty((C, n_it + 1), dtype=torch.float64).pin_memory(),
+           "steps": torch.empty((C, n_it + 1), dtype=torch.uint8).pin_memory(),
+           "blocks": torch.empty((C, n_it + 1, 4), dtype=torch.int32).pin_memory()}
+    batch = MCMC.ChainBatch(ch, rf, host_beds, [MCMC.philox_key(s, s) for s in seeds], device=dev)
+    ctx = batch.ctx
+    info = ctx.step_kernel_info()
+
+    # ---- (1) device-resident throughput: inputs already in HBM ---------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        batch.advance(n_it, want_caches=False)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
+    barrier()
+    l0 = ctx.launch_count()
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for k in range(a.steps):
+        batch.ctx.run(batch.bed, batch.mcres, batch.ssq, batch.seeds, batch.iteration, n_it, *batch._device_caches(n_it), 0,
+                      None, 4096)
+        batch.iteration += n_it
+        ev[k + 1].record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = ctx.launch_count() - l0
+    step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(a.steps)]
+    total_ms = ev[0].elapsed_time(ev[-1])
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * C * n_it * a.steps / (total_ms * 1e-3)
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # algorithmic HBM bytes of the timed launches: halo-tile read + old-residual read + accepted write-back
+    lc, st, bl = (t.cpu().numpy() for t in batch._device_caches(n_it))
+    ix, iy, bh, bw = (bl[..., k].astype(np.int64) for k in range(4))
+    ch_h = np.minimum(H, ix + bh // 2) - np.maximum(0, ix - bh // 2)
+    ch_w = np.minimum(W, iy + bw // 2) - np.maximum(0, iy - bw // 2)
+    bytes_last = (8 * ((ch_h + 2) * (ch_w + 2) + ch_h * ch_w) + st.astype(np.int64) * 16 * ch_h * ch_w).sum()
+    acc_rate = float(st.mean())
+    peak, peak_src = measured_peak()
+    launch_ms = float(np.mean(step_ms))
+    achieved = bytes_last / (step_ms[-1] * 1e-3) / 1e9
+    roofline = {"kernel": "run_kernel (fused K1 field synthesis + K4 Metropolis step)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_chain_step": float(bytes_last) / (C * n_it), "launch_ms": launch_ms,
+                "note": "U3 block-local formulation; this kernel is FP64/shared-memory bound, not HBM bound (DESIGN.md)"}
+
+    # ---- (2) the stencil metric: fused full-grid residual + masked loss (U2) and residual write (U1) ----------------
+    loss_d = torch.empty(C, dtype=torch.float64, device=dev)
+    res_d = batch.mcres
+
+    def time_call(fn, reps=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    scratch_res = torch.empty_like(batch.bed)
+    ms_u2 = time_call(lambda: ctx.residual_loss(batch.bed, None, loss_d, None))
+    ms_u1 = time_call(lambda: ctx.residual(batch.bed, scratch_res))
+    cells = C * H * W
+    stencil = {"U2_residual_loss": {"GBps": cells * 8 / (ms_u2 * 1e-3) / 1e9, "bytes_per_cell": 8, "ms": ms_u2},
+               "U1_residual": {"GBps": cells * 16 / (ms_u1 * 1e-3) / 1e9, "bytes_per_cell": 16, "ms": ms_u1}, "peak": peak}
+    for k in ("U2_residual_loss", "U1_residual"):
+        stencil[k]["frac"] = stencil[k]["GBps"] / peak
+    del scratch_res
+
+    # ---- (3) end to end through the public API: pinned host beds in, host results out, every step --------------------
+    for _ in range(2):
+        ch.run_many(n_it + 1, rf, host_beds, seeds, as_arrays=True, batch=batch, out=out, track_resampled=False)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        ch.run_many(n_it + 1, rf, host_beds, seeds, as_arrays=True, batch=batch, out=out, track_resampled=False)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_val = world * C * n_it * a.steps / (e2e_ms * 1e-3)
+    h2d = host_beds.numel() * 8
+    d2h = sum(t.numel() * t.element_size() for t in out.values())
+    sampler.stop()
+
+    # ---- (4) the one collective: ensemble mean/variance over all chains of all GPUs (outside the timed region) --------
+    ens = None
+    s1 = torch.empty((H, W), dtype=torch.float64, device=dev)
+    s2 = torch.empty_like(s1)
+    ref_bed = torch.as_tensor(g["bed0"]).to(dev)
+    ctx.ensemble_moments(batch.bed, ref_bed, s1, s2)
+    if world > 1:
+        dist.all_reduce(s1)
+        dist.all_reduce(s2)
+    n_tot = world * C
+    mean = ref_bed + s1 / n_tot
+    var = s2 / n_tot - (s1 / n_tot) ** 2
+    ens = {"chains": n_tot, "mean_abs_shift_m": float((mean - ref_bed).abs().mean().item()), "mean_std_m": float(var.clamp_min(0).sqrt().mean().item())}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        n_iter_cpu = a.cpu_iters or (1500 if a.grid <= 500 else 100)
+        v, cores, _ = cpu_arm(a.grid, n_iter_cpu, 1, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{cores} chains x {n_iter_cpu} iterations, numpy port of chain_crf.run (oracle/crf_oracle.py), one process per core, same {a.grid}x{a.grid} grid"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+                "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload_name(a), "grid": [H, W], "chains_per_gpu": C, "chains_total": world * C,
+                           "iters_per_step": n_it, "blocks": list(syn.BLOCKS), "field_model": "Matern nu=0.9 spectral",
+                           "l2": "state (bed+residual) %.2f GB per GPU >> 126 MB L2" % (2 * C * H * W * 8 / 1e9),
+                           "acceptance_rate": acc_rate, "step_kernel": info},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_ms / a.steps, "api": "chain_crf.run_many(pinned host beds -> host beds, loss/step/block caches)"},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stencil": stencil, "ensemble": ens,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_main(a)
+    else:
+        gpu_main(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -374,7 +374,7 @@ class chain_crf(chain):
             raise TypeError('The arugment "RF" has to be an object of the class RandField')
         if not hasattr(self, "rng_seed_int"):
             self.set_random_generator(None)
-        batch = ChainBatch(self, RF, np.asarray(self.initial_bed, dtype=np.float64)[None],
+        batch = ChainBatch(self, RF, np.ascontiguousarray(self.initial_bed, dtype=np.float64)[None],
                            [philox_key(self.rng_seed_int, RF.rng_seed_int)], iter0=self._philox_iter,
                            track_resampled=True)
         self._last_rf = RF
@@ -432,30 +432,37 @@ class chain_crf(chain):
         batch.close()
         return out + ((sample_values,) if sample_values is not None else ())
 
-    def run_many(self, n_iter, RF, initial_beds, rng_seeds, device=None, resync_every=4096, track_resampled=True):
+    def run_many(self, n_iter, RF, initial_beds, rng_seeds, device=None, resync_every=4096, track_resampled=True,
+                 as_arrays=False, batch=None, out=None):
         """Batched form: C independent chains (one per initial bed / seed) stepped concurrently on one GPU.
 
         Returns a list of the reference's 7-tuples (only_save_last_bed=True form), one per chain — what
-        largeScaleChain_mp collects from its worker processes (largeScaleChain_multiprocessing.py:78-79).
+        largeScaleChain_mp collects from its worker processes (largeScaleChain_multiprocessing.py:78-79) — or, with
+        as_arrays=True, a dict of stacked arrays (bed[C,H,W], loss[C,n], steps[C,n], blocks[C,n,4], resampled_times).
+        initial_beds: numpy [C,H,W] or a (pinned) CPU / CUDA torch tensor.  `batch` reuses the device buffers of a
+        previous call; `out` = dict of pinned CPU tensors (bed, loss, steps, blocks) to receive the results.
         """
         if not isinstance(RF, RandField):
             raise TypeError('The arugment "RF" has to be an object of the class RandField')
-        beds = np.ascontiguousarray(np.asarray(initial_beds, dtype=np.float64))
         keys = [philox_key(s, s) for s in rng_seeds]
-        batch = ChainBatch(self, RF, beds, keys, iter0=1, device=device, track_resampled=track_resampled)
-        C = beds.shape[0]
-        loss0 = batch.loss()
-        lc, st, bl = batch.advance(n_iter - 1, resync_every=resync_every)
-        final = batch.beds()
-        res_t = batch.resampled_times() if track_resampled else [np.zeros(beds.shape[1:])] * C
-        out = []
+        if batch is None:
+            batch = ChainBatch(self, RF, initial_beds, keys, iter0=1, device=device, track_resampled=track_resampled)
+        else:
+            batch.reset(initial_beds, keys, iter0=1)
+        C = batch.C
+        res = batch.advance_into(n_iter - 1, resync_every=resync_every, out=out)
+        if as_arrays:
+            res["batch"] = batch
+            return res
+        final, lc, st, bl = res["bed"], res["loss"], res["steps"], res["blocks"]
+        res_t = batch.resampled_times() if track_resampled else [np.zeros((batch.H, batch.W))] * C
+        outl = []
         for c in range(C):
-            loss = np.concatenate([[loss0[c]], lc[c]])
-            steps = np.concatenate([[0.0], st[c].astype(np.float64)])
-            blocks = np.vstack([np.full((1, 4), np.nan), bl[c].astype(np.float64)])
-            out.append((final[c], loss.copy(), np.zeros(n_iter), loss, steps, res_t[c], blocks))
+            loss = np.array(lc[c], dtype=np.float64)
+            outl.append((np.array(final[c]), loss.copy(), np.zeros(n_iter), loss, np.array(st[c], dtype=np.float64), res_t[c],
+                         np.array(bl[c], dtype=np.float64)))
         batch.close()
-        return out
+        return outl
 
 
 class ChainBatch:
@@ -465,28 +472,41 @@ class ChainBatch:
         import torch
         RF._require_spectral()
         self.torch = torch
-        beds = np.ascontiguousarray(initial_beds, dtype=np.float64)
-        if beds.ndim != 3 or beds.shape[1:] != chain_obj.xx.shape:
-            raise GmcShapeError(f"initial beds have shape {beds.shape}, expected [C,{chain_obj.xx.shape[0]},{chain_obj.xx.shape[1]}]")
-        self.C, self.H, self.W = beds.shape
-        if len(keys) != self.C:
-            raise ValueError("one seed per chain is required")
+        shape = tuple(initial_beds.shape)
+        if len(shape) != 3 or shape[1:] != chain_obj.xx.shape:
+            raise GmcShapeError(f"initial beds have shape {shape}, expected [C,{chain_obj.xx.shape[0]},{chain_obj.xx.shape[1]}]")
+        self.C, self.H, self.W = shape
         self.chain = chain_obj
         self.ctx = chain_obj._context(self.C, RF, device)
         dev = self.ctx.device
         self.dev = dev
         self.gate = np.asarray(chain_obj.region_mask if chain_obj.update_in_region else chain_obj.grounded_ice_mask)
-        self.bed = torch.as_tensor(beds).to(dev, non_blocking=False).contiguous()
+        self.bed = torch.empty(shape, dtype=torch.float64, device=dev)
         self.mcres = torch.empty_like(self.bed)
         self.ssq = torch.empty(self.C, dtype=torch.float64, device=dev)
         self._loss = torch.empty(self.C, dtype=torch.float64, device=dev)
-        self.seeds = keys_tensor(keys, dev)
-        self.resampled = torch.zeros((self.C, self.H, self.W), dtype=torch.int32, device=dev) if track_resampled else None
+        self.resampled = torch.zeros(shape, dtype=torch.int32, device=dev) if track_resampled else None
+        self._cache = None
+        self.reset(initial_beds, keys, iter0)
+
+    def reset(self, initial_beds, keys, iter0=1):
+        """(Re)load C initial beds (numpy, pinned CPU tensor or CUDA tensor) and recompute residual + loss (K2/K3)."""
+        torch = self.torch
+        if len(keys) != self.C:
+            raise ValueError("one seed per chain is required")
+        src = initial_beds if isinstance(initial_beds, torch.Tensor) else \
+            torch.as_tensor(np.ascontiguousarray(initial_beds, dtype=np.float64))
+        if tuple(src.shape) != (self.C, self.H, self.W) or src.dtype != torch.float64:
+            raise GmcShapeError(f"initial beds must be float64 [{self.C},{self.H},{self.W}]")
+        self.bed.copy_(src, non_blocking=True)
+        self.seeds = keys_tensor(keys, self.dev)
+        if self.resampled is not None:
+            self.resampled.zero_()
         self.iteration = int(iter0)
         self.ctx.residual_loss(self.bed, self.mcres, self._loss, self.ssq)
 
     def close(self):
-        self.bed = self.mcres = self.resampled = None
+        self.bed = self.mcres = self.resampled = self._cache = None
 
     def loss(self):
         return (self.ssq / (2 * self.chain.sigma_mc ** 2)).cpu().numpy()
@@ -503,20 +523,48 @@ class ChainBatch:
             raise GmcError("ChainBatch was created with track_resampled=False")
         return self.resampled.cpu().numpy().astype(np.float64) * self.gate[None].astype(np.float64)
 
+    def _device_caches(self, n):
+        torch = self.torch
+        if self._cache is None or self._cache[0].shape[1] != n:
+            self._cache = (torch.empty((self.C, n), dtype=torch.float64, device=self.dev),
+                           torch.empty((self.C, n), dtype=torch.uint8, device=self.dev),
+                           torch.empty((self.C, n, 4), dtype=torch.int32, device=self.dev))
+        return self._cache
+
     def advance(self, n_steps, resync_every=4096, want_caches=True):
         """n_steps fused free-running iterations (kernel K1+K4).  Returns (loss[C,n], accepted[C,n], blocks[C,n,4])."""
-        torch = self.torch
         lc = st = bl = None
         if want_caches:
-            lc = torch.empty((self.C, n_steps), dtype=torch.float64, device=self.dev)
-            st = torch.empty((self.C, n_steps), dtype=torch.uint8, device=self.dev)
-            bl = torch.empty((self.C, n_steps, 4), dtype=torch.int32, device=self.dev)
+            lc, st, bl = self._device_caches(n_steps)
         self.ctx.run(self.bed, self.mcres, self.ssq, self.seeds, self.iteration, n_steps, lc, st, bl, 0, self.resampled,
                      resync_every)
         self.iteration += n_steps
         if not want_caches:
             return None
         return lc.cpu().numpy(), st.cpu().numpy(), bl.cpu().numpy()
+
+    def advance_into(self, n_steps, resync_every=4096, out=None):
+        """The reference's per-chain outputs for a run of n_steps+1 iterations (index 0 = initial state, MCMC.py:1193-1199)
+        as stacked arrays; results land in the pinned tensors of `out` when given (one D2H copy each)."""
+        torch = self.torch
+        n = n_steps + 1
+        lc, st, bl = self._device_caches(n)
+        lc[:, 0] = self.ssq / (2 * self.chain.sigma_mc ** 2)
+        st[:, 0] = 0
+        bl[:, 0] = -1
+        self.ctx.run(self.bed, self.mcres, self.ssq, self.seeds, self.iteration, n_steps, lc, st, bl, 1, self.resampled,
+                     resync_every)
+        self.iteration += n_steps
+        if out is not None:
+            out["bed"].copy_(self.bed, non_blocking=True)
+            out["loss"].copy_(lc, non_blocking=True)
+            out["steps"].copy_(st, non_blocking=True)
+            out["blocks"].copy_(bl, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return dict(out)
+        blocks = bl.cpu().numpy().astype(np.float64)
+        blocks[:, 0, :] = np.nan                      # MCMC.py:1169: row 0 of blocks_cache stays NaN
+        return dict(bed=self.bed.cpu().numpy(), loss=lc.cpu().numpy(), steps=st.cpu().numpy(), blocks=blocks)
 
     def step_injected(self, fields, centres, us):
         """One step per chain with injected proposals.  Returns (accepted[C] bool, loss[C])."""
