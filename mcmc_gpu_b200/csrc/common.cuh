@@ -43,16 +43,18 @@ struct GmcFftPlan {
     int n_factors;
     int radix[GMC_MAX_FACTORS];   // stage order: radix[0] is the innermost (first executed) stage
     int tw_off;                   // offset (in double2) of exp(+2 pi i k / n), k in [0,n), in ctx->d_twiddle
+    int htw_off;                  // offset (in double2) of exp(+2 pi i k / (2n)), k in [0,n): real-row recombination
     int perm_off;                 // offset (in int16) into ctx->d_perm: position p holds logical index perm[p]
     int pos_off;                  // offset into ctx->d_pos: logical index k is stored at position pos[k]
-    int ksq_off;                  // offset (in double) of (2 pi fftfreq(n, d))^2 for k in [0, n/2] in ctx->d_ksq
 };
 
 // per block-size pair
 struct GmcPair {
-    int h, w;          // field shape [h][w] (rows, cols)
-    int plan_h, plan_w; // indices into ctx->plans
-    int64_t mask_off;  // offset (in double) of the taper in ctx->d_edge_masks
+    int h, w;            // field shape [h][w] (rows, cols)
+    int plan_h, plan_w2; // indices into ctx->plans: column transform of length h, row transform of length w/2
+    int pitchc;          // row pitch of the half plane in double2 units (>= w/2+1, odd)
+    int ksq_off_h, ksq_off_w;  // offsets (in double) of (2 pi fftfreq(n, d))^2, k in [0, n/2], for n = h and n = w
+    int64_t mask_off;    // offset (in double) of the taper in ctx->d_edge_masks
 };
 
 struct GmcFieldModel {
@@ -115,6 +117,7 @@ struct gmc_ctx {
     std::vector<GmcFftPlan> h_plans;
     int max_h, max_w;
     int step_smem_bytes;
+    int step_tile_off;     // offset (in doubles) of the candidate tile inside the step kernel's dynamic shared memory
     int step_ctas_per_sm;
     int64_t launches;
 };

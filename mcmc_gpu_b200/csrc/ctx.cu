@@ -59,6 +59,7 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->d_edge_masks = nullptr;
     c->max_h = c->max_w = 0;
     c->step_smem_bytes = 0;
+    c->step_tile_off = 0;
     c->step_ctas_per_sm = 0;
     c->launches = 0;
     c->dev.H = H;
@@ -205,6 +206,8 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
     std::vector<double2> tw;
     std::vector<int16_t> perm, pos;
     std::vector<double> ksq;
+    std::vector<std::pair<int, int>> ksq_index;   // (edge length, offset)
+    const long double two_pi = 2.0L * 3.14159265358979323846264338327950288L;
     auto plan_for = [&](int n) -> int {
         for (size_t i = 0; i < plans.size(); ++i)
             if (plans[i].n == n) return (int)i;
@@ -212,8 +215,12 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
         if (!factorize(n, p)) return -1;
         p.tw_off = (int)tw.size();
         for (int k = 0; k < n; ++k) {
-            // exp(+2 pi i k/n) with the argument reduced exactly before the libm call
-            const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+            const long double a = two_pi * (long double)k / (long double)n;
+            tw.push_back(make_double2((double)cosl(a), (double)sinl(a)));
+        }
+        p.htw_off = (int)tw.size();
+        for (int k = 0; k < n; ++k) {
+            const long double a = two_pi * (long double)k / (long double)(2 * n);
             tw.push_back(make_double2((double)cosl(a), (double)sinl(a)));
         }
         std::vector<int> cur(1, 0);
@@ -233,14 +240,20 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
             inv[cur[i]] = (int16_t)i;
         }
         pos.insert(pos.end(), inv.begin(), inv.end());
-        p.ksq_off = (int)ksq.size();
+        plans.push_back(p);
+        return (int)plans.size() - 1;
+    };
+    auto ksq_for = [&](int n) -> int {
+        for (auto& kv : ksq_index)
+            if (kv.first == n) return kv.second;
+        const int off = (int)ksq.size();
         const double val = 1.0 / (n * field_resolution);   // np.fft.fftfreq: val = 1.0/(n*d); results * val
         for (int i = 0; i <= n / 2; ++i) {
             const double kk = (double)i * val * 2 * M_PI;  // MCMC.py:221: fftfreq(...) * 2 * np.pi
             ksq.push_back(kk * kk);
         }
-        plans.push_back(p);
-        return (int)plans.size() - 1;
+        ksq_index.push_back({n, off});
+        return off;
     };
     int64_t total = 0;
     int mh = 0, mw = 0;
@@ -251,12 +264,16 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
         if (h > c->H || w > c->W)
             GMC_FAIL(GMC_ESHAPE, "gmc_set_blocks: pair %d (%dx%d) is larger than the %dx%d grid", i, h, w, c->H, c->W);
         if (w > 32767 || h > 32767) GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: block edge > 32767");
+        if (w / 2 / 2 + 1 > 64) GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: block width %d > 252 is not supported", w);
         pairs[i].h = h;
         pairs[i].w = w;
         pairs[i].plan_h = plan_for(h);
-        pairs[i].plan_w = plan_for(w);
-        if (pairs[i].plan_h < 0 || pairs[i].plan_w < 0)
+        pairs[i].plan_w2 = plan_for(w / 2);
+        if (pairs[i].plan_h < 0 || pairs[i].plan_w2 < 0)
             GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: pair %d (%dx%d) has a prime factor >= %d", i, h, w, GMC_MAX_RADIX);
+        pairs[i].pitchc = (w / 2 + 1) | 1;                 // odd pitch (in 16 B units): bank-conflict-free row pass
+        pairs[i].ksq_off_h = ksq_for(h);
+        pairs[i].ksq_off_w = ksq_for(w);
         pairs[i].mask_off = offsets[i];
         total = std::max<int64_t>(total, offsets[i] + (int64_t)h * w);
         mh = std::max(mh, h);

@@ -1,11 +1,16 @@
 // step.cu — K1 (proposal field synthesis) and K4 (Metropolis step) of the large-scale chain, fused.
 //
-// One CTA owns one chain.  Per iteration everything lives in shared memory: the h x w complex spectrum is filled
-// from counter-based Philox normals, inverse-transformed in place (mixed-radix decimation in time, digit-reversed
-// load), standardised and tapered into the proposal f (MCMC.py:176-254, 742-778); the candidate bed of the clipped
-// block plus a one-cell halo is staged as a tile, the residual is recomputed on the block only, the loss changes by
-// the block's delta, and the accept/reject decision plus in-place write-back happen without leaving the kernel
-// (MCMC.py:1263-1360).  HBM sees the bed halo tile, the old block residual and, on accept, the block write-back.
+// One CTA owns one chain.  Per iteration everything lives in shared memory:
+//   K1  the proposal f = taper * standardised Re(ifft2(noise * sqrt(S)))  (MCMC.py:176-254, 742-778).  Only the real part
+//       of the inverse transform is kept by the reference, so the spectrum is folded to its Hermitian part
+//       X_h(k) = (X(k) + conj(X(-k)))/2 and a complex-to-real inverse transform of the half plane [h][w/2+1] is run in
+//       place: column DFTs (mixed radix, decimation in time, digit-reversed load), a pair-recombination pass, and row DFTs
+//       of length w/2 whose complex output IS the real row (x[2m], x[2m+1]).  Mean and variance follow from the spectrum
+//       (DC term and Parseval), so standardisation is a scale factor applied before the row pass — no spatial reduction.
+//       With device RNG the Hermitian half plane is drawn directly (same distribution, half the normals).
+//   K4  the candidate bed of the clipped block plus a one-cell halo is staged as a tile, the residual is recomputed on the
+//       block only, the loss changes by the block's delta, and accept/reject plus in-place write-back happen without leaving
+//       the kernel (MCMC.py:1263-1360).  HBM sees the bed halo tile, the old block residual and, on accept, the write-back.
 #include "common.cuh"
 
 struct StepScalars {
@@ -13,6 +18,13 @@ struct StepScalars {
     int x0, x1, y0, y1, mx0, my0;
     double scale, nug, range_x, range_y, u;
     int accept;
+};
+
+// exact t / d for t * d < 2^32 with one multiply-high
+struct FastDiv {
+    uint32_t m, d;
+    __device__ __forceinline__ explicit FastDiv(int dd) : m(dd == 1 ? 0u : 0xFFFFFFFFu / (uint32_t)dd + 1u), d((uint32_t)dd) {}
+    __device__ __forceinline__ int div(int t) const { return d == 1 ? t : (int)__umulhi((uint32_t)t, m); }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -24,6 +36,7 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ double2 cmuli(double2 a) { return make_double2(-a.y, a.x); }   // a * (+i)
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
 
 // inverse-direction (e^{+i...}) DFT cores, in place on v[0..R)
 __device__ __forceinline__ void dft2(double2* v) {
@@ -90,26 +103,26 @@ __device__ __forceinline__ void dft_odd(double2* v, const double2* __restrict__ 
     }
 }
 
-// One radix-R stage over `count` independent lines.  ALONG_ROW: the transform runs along x (contiguous) and lanes
-// map to different rows (pitch is odd in double2 units => conflict-free); otherwise it runs along y and lanes map to
-// adjacent columns.
+// One radix-R decimation-in-time stage over `count` independent lines of length n, in place.
+// ALONG_ROW: the transform runs along x (contiguous) and lanes map to different rows (pitch is odd in double2 units =>
+// conflict-free); otherwise it runs along y and lanes map to adjacent columns.
 template <int R, bool ALONG_ROW>
 __device__ __forceinline__ void fft_stage(double2* Z, int pitch, int n, int count, int L, const double2* __restrict__ tw) {
     const int M = L / R;
     const int step = n / L;
     const int items = (n / R) * count;
+    const FastDiv dcount(count), dM(M);
     for (int t = threadIdx.x; t < items; t += GMC_STEP_THREADS) {
-        const int line = t % count;
-        const int bf = t / count;
-        const int blk = bf / M, k1 = bf - blk * M;
+        const int bf = dcount.div(t);
+        const int line = t - bf * count;
+        const int blk = dM.div(bf), k1 = bf - blk * M;
         const int base = blk * L + k1;
+        double2* p0 = ALONG_ROW ? Z + line * pitch + base : Z + base * pitch + line;
+        const int stride = ALONG_ROW ? M : M * pitch;
         double2 v[R];
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int p = base + q * M;
-            v[q] = ALONG_ROW ? Z[line * pitch + p] : Z[p * pitch + line];
-        }
-        if (L > R) {   // first stage has all twiddles == 1
+        for (int q = 0; q < R; ++q) v[q] = p0[q * stride];
+        if (L > R) {   // the first stage has all twiddles == 1
             const int i1 = k1 * step;
             int iq = i1;
 #pragma unroll
@@ -124,15 +137,11 @@ __device__ __forceinline__ void fft_stage(double2* Z, int pitch, int n, int coun
         else if (R == 8) dft8(v);
         else dft_odd<R>(v, tw, n / R);
 #pragma unroll
-        for (int q = 0; q < R; ++q) {
-            const int p = base + q * M;
-            if (ALONG_ROW) Z[line * pitch + p] = v[q];
-            else Z[p * pitch + line] = v[q];
-        }
+        for (int q = 0; q < R; ++q) p0[q * stride] = v[q];
     }
 }
 
-// Fallback for any other prime radix R <= GMC_MAX_RADIX (block edges such as 58 = 2*29): O(R^2) per butterfly with the
+// Fallback for any other prime radix R < GMC_MAX_RADIX (block edges such as 58 = 2*29): O(R^2) per butterfly with the
 // inputs parked in local memory.  Slow but rare; the default block sizes never take it.
 template <bool ALONG_ROW>
 __device__ __noinline__ void fft_stage_generic(double2* Z, int pitch, int n, int count, int L, int R,
@@ -247,110 +256,156 @@ __device__ __forceinline__ double spec_amp(const SpecParams& sp, double ksq_sum)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1: synthesise one field into shared memory.  On return (after its final __syncthreads) buf[0 .. h*w) holds
-// f[h][w] row-major (tapered when apply_taper).
+// K1: synthesise one field into shared memory.  On return (after its final __syncthreads) the standardised field times
+// `scale` sits in buf as F[y * fpitch + x] with fpitch = 2 * pitchc doubles (rows are the complex rows of the half plane).
+// Nugget noise and taper are applied by the consumer (field_value()).
 // ---------------------------------------------------------------------------------------------------------------
+struct FieldView {
+    const double* F;        // shared memory
+    int fpitch;
+    int w;
+    double sq_nug;          // sqrt(nug); 0 => no nugget term
+    const double* taper;    // global [h][w] or nullptr
+    const double* z_nug;    // injected unit normals [h][w] or nullptr (=> Philox)
+};
+
 template <bool INJECT>
-__device__ void synth_field(const GmcDev& d, double* buf, double* scratch, int pair_idx, double scale, double nug,
-                            double range_x, double range_y, const Philox& rng, uint32_t it_lo, uint32_t it_hi,
-                            const double* __restrict__ z_re, const double* __restrict__ z_im,
-                            const double* __restrict__ z_nug, bool apply_taper) {
+__device__ __forceinline__ double field_value(const FieldView& fv, int y, int x, const Philox& rng, uint32_t it_lo,
+                                              uint32_t it_hi) {
+    double f = fv.F[y * fv.fpitch + x];
+    if (fv.sq_nug > 0.0) {                                                            // MCMC.py:250
+        const int e = y * fv.w + x;
+        double z0, z1;
+        if (INJECT) z0 = fv.z_nug[e];
+        else box_muller(rng((uint32_t)e, it_lo, it_hi, GMC_STREAM_NUGGET), z0, z1);
+        f = add_rn(f, mul_rn(fv.sq_nug, z0));
+    }
+    if (fv.taper) f = mul_rn(f, __ldg(fv.taper + y * fv.w + x));                       // MCMC.py:778
+    return f;
+}
+
+template <bool INJECT>
+__device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, int pair_idx, double scale, double nug,
+                                 double range_x, double range_y, const Philox& rng, uint32_t it_lo, uint32_t it_hi,
+                                 const double* __restrict__ z_re, const double* __restrict__ z_im,
+                                 const double* __restrict__ z_nug, bool apply_taper) {
     __shared__ GmcFftPlan s_plan[2];
     const GmcPair pr = d.pairs[pair_idx];
-    const int h = pr.h, w = pr.w;
-    if (threadIdx.x < 2) s_plan[threadIdx.x] = d.plans[threadIdx.x == 0 ? pr.plan_h : pr.plan_w];
+    const int h = pr.h, w = pr.w, n2 = w / 2, hc = n2 + 1, pitchc = pr.pitchc;
+    if (threadIdx.x < 2) s_plan[threadIdx.x] = d.plans[threadIdx.x == 0 ? pr.plan_h : pr.plan_w2];
     __syncthreads();
     const GmcFftPlan& ph = s_plan[0];
     const GmcFftPlan& pw = s_plan[1];
-    const int pitch = w + 1;
     double2* Z = reinterpret_cast<double2*>(buf);
     const SpecParams sp = make_spec(d.fm, range_x, range_y);
     const int16_t* posY = d.pos + ph.pos_off;
-    const int16_t* posX = d.pos + pw.pos_off;
-    const double* ksqY = d.ksq + ph.ksq_off;
-    const double* ksqX = d.ksq + pw.ksq_off;
+    const double* ksqY = d.ksq + pr.ksq_off_h;
+    const double* ksqX = d.ksq + pr.ksq_off_w;
+    const double inv_sqrt2 = 0.70710678118654752440;
 
-    // (1) fill the spectrum: one item per (|ky|, |kx|) class, up to four mirrored entries share sqrt(S)
-    const int hq = h / 2 + 1, wq = w / 2 + 1;
-    for (int q = threadIdx.x; q < hq * wq; q += GMC_STEP_THREADS) {
-        const int a = q / wq, b = q - a * wq;
+    // (1) fill the Hermitian half plane (ky in [0,h), kx in [0,w/2]) at the digit-reversed row position of the column
+    // pass; one item per (|ky| = a, kx): the entries ky = a and ky = h-a share sqrt(S).  Accumulate the power for the
+    // variance (Parseval): interior columns count twice (their mirror images kx > w/2 are not stored).
+    double power = 0.0;
+    const FastDiv dhc(hc);
+    for (int q = threadIdx.x; q < (h / 2 + 1) * hc; q += GMC_STEP_THREADS) {
+        const int a = dhc.div(q), kx = q - a * hc;
         // MCMC.py:224: k = sqrt(kxv**2 + kyv**2) + 1e-10
-        const double amp = spec_amp(sp, add_rn(__ldg(ksqX + b), __ldg(ksqY + a)));
-        const int na = (a == 0 || a == h / 2) ? 1 : 2;
-        const int nb = (b == 0 || b == w / 2) ? 1 : 2;
-        for (int sa = 0; sa < na; ++sa) {
-            const int ky = sa ? h - a : a;
-            for (int sb = 0; sb < nb; ++sb) {
-                const int kx = sb ? w - b : b;
-                const int e = ky * w + kx;
-                double zr, zi;
-                if (INJECT) {
-                    zr = z_re[e];
-                    zi = z_im[e];
-                } else {
-                    box_muller(rng((uint32_t)e, it_lo, it_hi, GMC_STREAM_NOISE), zr, zi);
-                }
-                Z[__ldg(posY + ky) * pitch + __ldg(posX + kx)] = make_double2(zr * amp, zi * amp);
+        const double amp = spec_amp(sp, add_rn(__ldg(ksqX + kx), __ldg(ksqY + a)));
+        const bool self_y = (a == 0 || 2 * a == h);
+        const bool edge_x = (kx == 0 || kx == n2);
+        const int a2 = self_y ? a : h - a;
+        double2 X0, X1;
+        if (INJECT) {
+            // X_h(k) = sqrt(S)/2 * ((A_k + A_-k) + i (B_k - B_-k)),  -k = ((h-ky)%h, (w-kx)%w)
+            const int kxm = (kx == 0) ? 0 : w - kx;
+            const int e0 = a * w + kx, m0 = ((a == 0) ? 0 : h - a) * w + kxm;
+            const int e1 = a2 * w + kx, m1 = ((a2 == 0) ? 0 : h - a2) * w + kxm;
+            X0 = make_double2(0.5 * amp * (z_re[e0] + z_re[m0]), 0.5 * amp * (z_im[e0] - z_im[m0]));
+            X1 = make_double2(0.5 * amp * (z_re[e1] + z_re[m1]), 0.5 * amp * (z_im[e1] - z_im[m1]));
+        } else {
+            double z0, z1;
+            box_muller(rng((uint32_t)(a * w + kx), it_lo, it_hi, GMC_STREAM_NOISE), z0, z1);
+            if (self_y && edge_x) {
+                X0 = make_double2(amp * z0, 0.0);                  // self-conjugate point: real, variance S
+                X1 = X0;
+            } else {
+                X0 = make_double2(amp * inv_sqrt2 * z0, amp * inv_sqrt2 * z1);
+                if (edge_x) X1 = cconj(X0);                        // columns kx = 0, w/2 are Hermitian in ky
+                else if (!self_y) {
+                    box_muller(rng((uint32_t)(a2 * w + kx), it_lo, it_hi, GMC_STREAM_NOISE), z0, z1);
+                    X1 = make_double2(amp * inv_sqrt2 * z0, amp * inv_sqrt2 * z1);
+                } else X1 = X0;
             }
         }
+        if (a == 0 && kx == 0) X0 = X1 = make_double2(0.0, 0.0);   // DC: removed by the mean subtraction (MCMC.py:248)
+        const double wgt = edge_x ? 1.0 : 2.0;
+        power += wgt * (X0.x * X0.x + X0.y * X0.y);
+        Z[__ldg(posY + a) * pitchc + kx] = X0;
+        if (!self_y) {
+            power += wgt * (X1.x * X1.x + X1.y * X1.y);
+            Z[__ldg(posY + a2) * pitchc + kx] = X1;
+        }
     }
-    __syncthreads();
+    power = block_sum<GMC_STEP_THREADS>(power, scratch);           // also orders the fill before the column pass
+    // field = (1/(hw)) sum_k X_h e^{...};  var = power/(hw)^2;  (x - mean)/(std + 1e-12) * scale   MCMC.py:247-250
+    const double inv_n = 1.0 / ((double)h * (double)w);
+    const double sd = sqrt(power) * inv_n;
+    const double cscale = scale / (sd + 1e-12) * inv_n;
 
-    // (2) inverse 2-D DFT in place: last axis first like numpy's ifft2
-    fft_lines<true>(Z, pitch, pw, h, d.twiddle);
-    fft_lines<false>(Z, pitch, ph, w, d.twiddle);
+    // (2) inverse DFT along y for the w/2+1 stored columns
+    fft_lines<false>(Z, pitchc, ph, hc, d.twiddle);
 
-    // (3) standardise: (x - mean) / (std + 1e-12), population std                       MCMC.py:247-248
-    const int n = h * w;
-    const double inv_n = 1.0 / (double)n;
-    double acc = 0.0;
-    for (int e = threadIdx.x; e < n; e += GMC_STEP_THREADS) {
-        const int y = e / w, x = e - y * w;
-        acc += Z[y * pitch + x].x;
-    }
-    const double mean = block_sum<GMC_STEP_THREADS>(acc, scratch) * inv_n * inv_n;   // includes the 1/(h w) of ifft2
-    acc = 0.0;
-    for (int e = threadIdx.x; e < n; e += GMC_STEP_THREADS) {
-        const int y = e / w, x = e - y * w;
-        const double dv = Z[y * pitch + x].x * inv_n - mean;
-        acc += dv * dv;
-    }
-    const double sd = sqrt(block_sum<GMC_STEP_THREADS>(acc, scratch) * inv_n);
-    const double inv_sd = 1.0 / (sd + 1e-12);
-    const double sq_nug = sqrt(nug);
-    const double* taper = d.edge_masks + pr.mask_off;
-
-    // (4) scale, nugget, taper, and compact the real parts to buf[0..n) in ascending waves (in-place safe: the
-    // destination of element e only overlaps sources of elements <= e/2, all read in this or an earlier wave)
-    constexpr int CH = 8;
-    for (int wave = 0; wave * CH * GMC_STEP_THREADS < n; ++wave) {
-        double v[CH];
+    // (3) real-row recombination: Y_k = (X_k + conj X_{n2-k}) + i (X_k - conj X_{n2-k}) e^{+2 pi i k/w}, k < n2, stored
+    // at the digit-reversed position of the row pass.  One warp per row; a lane owns the pair (k, n2-k), reads both, and
+    // only then writes, so the in-place permutation is safe (npairs <= 64).
+    {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        const int16_t* posW = d.pos + pw.pos_off;
+        const double2* htw = d.twiddle + pw.htw_off;
+        const int npairs = n2 / 2 + 1;
+        for (int y = wid; y < h; y += GMC_STEP_THREADS / 32) {
+            double2* row = Z + y * pitchc;
+            double2 ya[2], yb[2];
+            int ka[2], kb[2];
 #pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            const int e = (wave * CH + k) * GMC_STEP_THREADS + threadIdx.x;
-            if (e < n) {
-                const int y = e / w, x = e - y * w;
-                double f = (Z[y * pitch + x].x * inv_n - mean) * inv_sd;
-                double nz = 0.0;
-                if (nug > 0.0) {
-                    double z0, z1;
-                    if (INJECT) z0 = z_nug[e];
-                    else box_muller(rng((uint32_t)e, it_lo, it_hi, GMC_STREAM_NUGGET), z0, z1);
-                    nz = sq_nug * z0;
+            for (int it = 0; it < 2; ++it) {
+                const int k = lane + 32 * it;
+                ka[it] = kb[it] = -1;
+                if (k < npairs) {
+                    const int kp = n2 - k;                         // partner (k = 0 pairs with the Nyquist entry n2)
+                    const double2 xk = row[k], xp = row[kp];
+                    const double2 E = cadd(xk, cconj(xp));
+                    const double2 O = cmul(csub(xk, cconj(xp)), (k == 0) ? make_double2(1.0, 0.0) : __ldg(htw + k));
+                    ya[it] = make_double2((E.x - O.y) * cscale, (E.y + O.x) * cscale);          // E + iO
+                    ka[it] = k;
+                    if (k != 0 && kp != k) {
+                        yb[it] = make_double2((E.x + O.y) * cscale, (-E.y + O.x) * cscale);     // conj(E) + i conj(O)
+                        kb[it] = kp;
+                    }
                 }
-                f = add_rn(mul_rn(f, scale), nz);                                     // MCMC.py:250
-                if (apply_taper) f = mul_rn(f, __ldg(taper + e));                     // MCMC.py:778
-                v[k] = f;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                if (ka[it] >= 0) row[__ldg(posW + ka[it])] = ya[it];
+                if (kb[it] >= 0) row[__ldg(posW + kb[it])] = yb[it];
             }
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            const int e = (wave * CH + k) * GMC_STEP_THREADS + threadIdx.x;
-            if (e < n) buf[e] = v[k];
-        }
-        __syncthreads();
     }
+
+    // (4) inverse DFT of length w/2 along x: row y now holds (f[y][2m], f[y][2m+1]) as its m-th complex entry
+    fft_lines<true>(Z, pitchc, pw, h, d.twiddle);
+
+    FieldView fv;
+    fv.F = buf;
+    fv.fpitch = 2 * pitchc;
+    fv.w = w;
+    fv.sq_nug = (nug > 0.0) ? sqrt(nug) : 0.0;
+    fv.taper = apply_taper ? d.edge_masks + pr.mask_off : nullptr;
+    fv.z_nug = z_nug;
+    return fv;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -369,32 +424,69 @@ __device__ __forceinline__ void block_window(StepScalars& s, int H, int W) {
 
 __device__ __forceinline__ double sq_or_zero(double v) { return (v == v) ? mul_rn(v, v) : 0.0; }
 
-// f: [h][w] with row pitch f_pitch (shared or global).  tile: (bh+2)x(bw+2) doubles; newres: bh*bw doubles (may alias f
-// only if f is dead after the tile is built, which holds: f is read in phase A only).
-__device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, const double* f, int f_pitch, double* tile,
-                          double* newres, double* bed, double* mcres, double& ssq, int32_t* resampled,
-                          double* loss_next_out) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Pull the lines the tail will read (bed halo tile, old block residual) from HBM into L2 while the field is synthesised.
+__device__ __forceinline__ void prefetch_block(const StepScalars& s, int H, int W, const double* bed, const double* mcres) {
+    const int r0 = max(s.x0 - 1, 0), r1 = min(s.x1 + 1, H);
+    const int c0 = max(s.y0 - 1, 0), c1 = min(s.y1 + 1, W);
+    const int lines = ((c1 - c0) * 8 + 127) / 128 + 1;     // 128 B lines per row segment (+1: unaligned start)
+    const int total = (r1 - r0) * lines;
+    for (int t = threadIdx.x; t < 2 * total; t += GMC_STEP_THREADS) {
+        const int which = t >= total;
+        const int u = which ? t - total : t;
+        const int r = u / lines, l = u - r * lines;
+        const double* base = (which ? mcres : bed) + (int64_t)(r0 + r) * W + c0;
+        const char* p = reinterpret_cast<const char*>(base) + l * 128;
+        if (p < reinterpret_cast<const char*>(base + (c1 - c0))) prefetch_l2(p);
+    }
+}
+
+// Field source for the tail: either the synthesised field in shared memory (FieldView) or an injected f in global memory.
+template <bool INJECT_F>
+__device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, const FieldView& fv, const double* f_inj,
+                          int f_pitch, const Philox& rng, uint32_t it_lo, uint32_t it_hi, double* tile, double* newres,
+                          double* bed, double* mcres, double& ssq, int32_t* resampled, double* loss_next_out) {
     const int H = d.H, W = d.W;
     const StepScalars s = *sc;
     const int bh = s.x1 - s.x0, bw = s.y1 - s.y0;
     const int tp = bw + 2;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    const FastDiv dtp(tp), dbw(bw);
 
     // phase A: candidate tile = block + one-cell halo                                  MCMC.py:1279-1290
-    for (int t = threadIdx.x; t < (bh + 2) * tp; t += GMC_STEP_THREADS) {
-        const int ti = t / tp, tj = t - ti * tp;
-        const int i = s.x0 - 1 + ti, j = s.y0 - 1 + tj;
-        double v = qnan;
-        if (i >= 0 && i < H && j >= 0 && j < W) {
-            const int64_t idx = (int64_t)i * W + j;
-            v = __ldcg(bed + idx);
-            if (ti >= 1 && ti <= bh && tj >= 1 && tj <= bw && (__ldg(d.flags + idx) & FLAG_GATE)) {
-                double p = f[(s.mx0 + ti - 1) * f_pitch + (s.my0 + tj - 1)];
-                if (d.crf_weight) p = mul_rn(p, __ldg(d.crf_weight + idx));
-                v = add_rn(v, p);
+    {
+        constexpr int U = 4;
+        const int n_tile = (bh + 2) * tp;
+        for (int t0 = threadIdx.x; t0 < n_tile; t0 += U * GMC_STEP_THREADS) {
+            double v[U];
+            uint8_t fl[U];
+            int64_t idx[U];
+            int ti[U], tj[U];
+#pragma unroll
+            for (int k = 0; k < U; ++k) {                     // issue all loads of the batch first
+                const int t = t0 + k * GMC_STEP_THREADS;
+                ti[k] = dtp.div(t);
+                tj[k] = t - ti[k] * tp;
+                const int i = s.x0 - 1 + ti[k], j = s.y0 - 1 + tj[k];
+                const bool in = t < n_tile && i >= 0 && i < H && j >= 0 && j < W;
+                idx[k] = in ? (int64_t)i * W + j : -1;
+                v[k] = in ? __ldcg(bed + idx[k]) : qnan;
+                fl[k] = in ? __ldg(d.flags + idx[k]) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < U; ++k) {
+                const int t = t0 + k * GMC_STEP_THREADS;
+                if (t >= n_tile) break;
+                if (idx[k] >= 0 && ti[k] >= 1 && ti[k] <= bh && tj[k] >= 1 && tj[k] <= bw && (fl[k] & FLAG_GATE)) {
+                    const int fy = s.mx0 + ti[k] - 1, fx = s.my0 + tj[k] - 1;
+                    double p = INJECT_F ? f_inj[fy * f_pitch + fx] : field_value<false>(fv, fy, fx, rng, it_lo, it_hi);
+                    if (d.crf_weight) p = mul_rn(p, __ldg(d.crf_weight + idx[k]));
+                    v[k] = add_rn(v[k], p);
+                }
+                tile[t] = v[k];
             }
         }
-        tile[t] = v;
     }
     __syncthreads();
 
@@ -402,39 +494,40 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
     double delta = 0.0;
     int bad = 0;
     for (int e = threadIdx.x; e < bh * bw; e += GMC_STEP_THREADS) {
-        const int bi = e / bw, bj = e - bi * bw;
+        const int bi = dbw.div(e), bj = e - bi * bw;
         const int i = s.x0 + bi, j = s.y0 + bj;
         const int64_t idx = (int64_t)i * W + j;
         const double* tc = tile + (bi + 1) * tp + (bj + 1);
-        double dx, dy;
-        {
-            int jl = j - 1, jr = j + 1;
-            double den = d.two_res;
-            if (j == 0) { jl = 0; den = d.res; }
-            else if (j == W - 1) { jr = W - 1; den = d.res; }
-            const int64_t r = (int64_t)i * W;
-            const double fr = mul_rn(__ldg(d.velx + r + jr), sub_rn(__ldg(d.surf + r + jr), tc[jr - j]));
-            const double fl = mul_rn(__ldg(d.velx + r + jl), sub_rn(__ldg(d.surf + r + jl), tc[jl - j]));
-            dx = div_rn(sub_rn(fr, fl), den);
-        }
-        {
-            int iu = i - 1, id = i + 1;
-            double den = d.two_res;
-            if (i == 0) { iu = 0; den = d.res; }
-            else if (i == H - 1) { id = H - 1; den = d.res; }
-            const double fd = mul_rn(__ldg(d.vely + (int64_t)id * W + j), sub_rn(__ldg(d.surf + (int64_t)id * W + j), tc[(id - i) * tp]));
-            const double fu = mul_rn(__ldg(d.vely + (int64_t)iu * W + j), sub_rn(__ldg(d.surf + (int64_t)iu * W + j), tc[(iu - i) * tp]));
-            dy = div_rn(sub_rn(fd, fu), den);
-        }
-        const double rnew = sub_rn(add_rn(add_rn(dx, dy), __ldg(d.dhdt + idx)), __ldg(d.smb + idx));
-        newres[e] = rnew;
+        int jl = j - 1, jr = j + 1;
+        double denx = d.two_res;
+        if (j == 0) { jl = 0; denx = d.res; }
+        else if (j == W - 1) { jr = W - 1; denx = d.res; }
+        int iu = i - 1, id = i + 1;
+        double deny = d.two_res;
+        if (i == 0) { iu = 0; deny = d.res; }
+        else if (i == H - 1) { id = H - 1; deny = d.res; }
+        const int64_t r = (int64_t)i * W;
+        // all global loads first
+        const double vxr = __ldg(d.velx + r + jr), sxr = __ldg(d.surf + r + jr);
+        const double vxl = __ldg(d.velx + r + jl), sxl = __ldg(d.surf + r + jl);
+        const double vyd = __ldg(d.vely + (int64_t)id * W + j), syd = __ldg(d.surf + (int64_t)id * W + j);
+        const double vyu = __ldg(d.vely + (int64_t)iu * W + j), syu = __ldg(d.surf + (int64_t)iu * W + j);
+        const double dh = __ldg(d.dhdt + idx), sm = __ldg(d.smb + idx), sc0 = __ldg(d.surf + idx);
         const uint8_t fl = __ldg(d.flags + idx);
+        const double rold = __ldcg(mcres + idx);
+        const double fr = mul_rn(vxr, sub_rn(sxr, tc[jr - j]));
+        const double fl_ = mul_rn(vxl, sub_rn(sxl, tc[jl - j]));
+        const double dx = div_rn(sub_rn(fr, fl_), denx);
+        const double fd = mul_rn(vyd, sub_rn(syd, tc[(id - i) * tp]));
+        const double fu = mul_rn(vyu, sub_rn(syu, tc[(iu - i) * tp]));
+        const double dy = div_rn(sub_rn(fd, fu), deny);
+        const double rnew = sub_rn(add_rn(add_rn(dx, dy), dh), sm);
+        newres[e] = rnew;
         if (fl & FLAG_MC) {
-            const double rold = __ldcg(mcres + idx);
             if (rnew == rnew && rold == rold) delta += (rnew - rold) * (rnew + rold);
             else delta += sq_or_zero(rnew) - sq_or_zero(rold);
         }
-        if ((fl & FLAG_GATE) && sub_rn(__ldg(d.surf + idx), tc[0]) <= 0.0) bad = 1;
+        if ((fl & FLAG_GATE) && sub_rn(sc0, tc[0]) <= 0.0) bad = 1;
     }
     const double dsum = block_sum<GMC_STEP_THREADS>(delta, scratch);
     bad = __syncthreads_or(bad);
@@ -461,7 +554,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
     if (accept) {
         ssq = scratch[34];
         for (int e = threadIdx.x; e < bh * bw; e += GMC_STEP_THREADS) {
-            const int bi = e / bw, bj = e - bi * bw;
+            const int bi = dbw.div(e), bj = e - bi * bw;
             const int64_t idx = (int64_t)(s.x0 + bi) * W + (s.y0 + bj);
             __stcg(bed + idx, tile[(bi + 1) * tp + (bj + 1)]);
             __stcg(mcres + idx, newres[e]);
@@ -490,7 +583,7 @@ extern __shared__ __align__(16) unsigned char gmc_smem[];
 __global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
     run_kernel(GmcDev d, double* bed_all, double* mcres_all, double* ssq_all, const uint64_t* __restrict__ seeds,
                uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache,
-               int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int resync_every) {
+               int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int resync_every, int tile_off) {
     __shared__ double scratch[40];
     __shared__ StepScalars sc;
     double* buf = reinterpret_cast<double*>(gmc_smem);
@@ -537,18 +630,17 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
             block_window(sc, d.H, d.W);
         }
         __syncthreads();
-        synth_field<false>(d, buf, scratch, sc.pair, sc.scale, sc.nug, sc.range_x, sc.range_y, rng, it_lo, it_hi, nullptr,
-                           nullptr, nullptr, true);
-        const int n = sc.h * sc.w;
-        step_tail(d, &sc, scratch, buf, sc.w, buf + n, buf, bed, mcres, ssq, resampled, nullptr);
+        prefetch_block(sc, d.H, d.W, bed, mcres);
+        const FieldView fv = synth_field<false>(d, buf, scratch, sc.pair, sc.scale, sc.nug, sc.range_x, sc.range_y, rng, it_lo,
+                                                it_hi, nullptr, nullptr, nullptr, true);
+        // tile after the field; the new residuals reuse the field's storage once the tile is built (f is dead by then)
+        step_tail<false>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
+                         nullptr);
         if (threadIdx.x == 0) {
             const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
             if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
             if (step_cache) step_cache[slot] = (uint8_t)sc.accept;
-            if (blocks_cache) {
-                int4 b = make_int4(sc.ix, sc.iy, sc.h, sc.w);
-                reinterpret_cast<int4*>(blocks_cache)[slot] = b;
-            }
+            if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(sc.ix, sc.iy, sc.h, sc.w);
         }
         __syncthreads();
     }
@@ -576,9 +668,11 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS)
     }
     __syncthreads();
     double ssq = ssq_all[c];
-    step_tail(d, &sc, scratch, f_all + c * f_stride, sc.w, buf + (int64_t)hmax * wmax, buf, bed_all + c * plane,
-              mcres_all + c * plane, ssq, resampled_all ? resampled_all + c * plane : nullptr,
-              loss_next_out ? loss_next_out + c : nullptr);
+    const Philox rng(0ull);
+    FieldView fv = {};
+    step_tail<true>(d, &sc, scratch, fv, f_all + c * f_stride, sc.w, rng, 0u, 0u, buf + (int64_t)hmax * wmax, buf,
+                    bed_all + c * plane, mcres_all + c * plane, ssq, resampled_all ? resampled_all + c * plane : nullptr,
+                    loss_next_out ? loss_next_out + c : nullptr);
     if (threadIdx.x == 0) {
         ssq_all[c] = ssq;
         if (accepted_out) accepted_out[c] = (uint8_t)sc.accept;
@@ -597,25 +691,33 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
     const int i = blockIdx.x;
     const int p = pair[i];
     const Philox rng(INJECT ? 0ull : seeds[i]);
-    synth_field<INJECT>(d, buf, scratch, p, scale[i], nug[i], range_x[i], range_y[i], rng, (uint32_t)iter,
-                        (uint32_t)(iter >> 32), INJECT ? z_re + i * stride : nullptr, INJECT ? z_im + i * stride : nullptr,
-                        INJECT ? z_nug + i * stride : nullptr, apply_taper != 0);
-    const int n = d.pairs[p].h * d.pairs[p].w;
-    for (int e = threadIdx.x; e < n; e += GMC_STEP_THREADS) f_out[i * stride + e] = buf[e];
+    const uint32_t it_lo = (uint32_t)iter, it_hi = (uint32_t)(iter >> 32);
+    const FieldView fv = synth_field<INJECT>(d, buf, scratch, p, scale[i], nug[i], range_x[i], range_y[i], rng, it_lo, it_hi,
+                                             INJECT ? z_re + i * stride : nullptr, INJECT ? z_im + i * stride : nullptr,
+                                             INJECT ? z_nug + i * stride : nullptr, apply_taper != 0);
+    const int h = d.pairs[p].h, w = d.pairs[p].w;
+    const FastDiv dw(w);
+    for (int e = threadIdx.x; e < h * w; e += GMC_STEP_THREADS) {
+        const int y = dw.div(e), x = e - y * w;
+        f_out[i * stride + e] = field_value<INJECT>(fv, y, x, rng, it_lo, it_hi);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // host entry points
 // ---------------------------------------------------------------------------------------------------------------
-static size_t tail_bytes(int h, int w) { return ((size_t)h * w + (size_t)(h + 2) * (w + 2)) * sizeof(double); }
+static size_t tile_bytes(int h, int w) { return (size_t)(h + 2) * (w + 2) * sizeof(double); }
+static size_t field_bytes(const GmcPair& p) { return (size_t)p.h * p.pitchc * sizeof(double2); }
 
 int gmc_step_configure(gmc_ctx* c) {
-    size_t need = 0;
+    // layout: [ field / new residuals | tile ]; the tile starts after the largest field so one offset serves all pairs
+    size_t fmax = 0, tmax = 0;
     for (const GmcPair& p : c->h_pairs) {
-        const size_t z = (size_t)p.h * (p.w + 1) * sizeof(double2);
-        need = std::max(need, std::max(z, tail_bytes(p.h, p.w)));
+        fmax = std::max(fmax, field_bytes(p));
+        tmax = std::max(tmax, tile_bytes(p.h, p.w));
     }
-    need = (need + 15) & ~(size_t)15;
+    fmax = (fmax + 15) & ~(size_t)15;
+    const size_t need = fmax + ((tmax + 15) & ~(size_t)15);
     cudaDeviceProp prop;
     GMC_CUDA(cudaGetDeviceProperties(&prop, c->device));
     if (need > prop.sharedMemPerBlockOptin)
@@ -625,6 +727,7 @@ int gmc_step_configure(gmc_ctx* c) {
     GMC_CUDA(cudaFuncSetAttribute(field_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     GMC_CUDA(cudaFuncSetAttribute(field_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     c->step_smem_bytes = (int)need;
+    c->step_tile_off = (int)(fmax / sizeof(double));
     int nb = 0;
     GMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, run_kernel, GMC_STEP_THREADS, need));
     c->step_ctas_per_sm = nb;
@@ -674,7 +777,7 @@ extern "C" int gmc_step_injected(gmc_ctx* c, double* bed, double* mcres, double*
     if (hmax < 2 || wmax < 2 || hmax > c->H || wmax > c->W)
         GMC_FAIL(GMC_ESHAPE, "gmc_step_injected: hmax x wmax = %dx%d must lie in [2, grid %dx%d]", hmax, wmax, c->H, c->W);
     if (f_stride < (int64_t)hmax * wmax) GMC_FAIL(GMC_ESHAPE, "gmc_step_injected: f_stride smaller than hmax*wmax");
-    const size_t smem = (tail_bytes(hmax, wmax) + 15) & ~(size_t)15;
+    const size_t smem = (((size_t)hmax * wmax * sizeof(double) + tile_bytes(hmax, wmax)) + 15) & ~(size_t)15;
     cudaDeviceProp prop;
     GMC_CUDA(cudaGetDeviceProperties(&prop, c->device));
     if (smem > prop.sharedMemPerBlockOptin)
@@ -702,7 +805,7 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
     run_kernel<<<C, GMC_STEP_THREADS, c->step_smem_bytes, (cudaStream_t)stream>>>(c->dev, bed, mcres, ssq, seeds, iter0, n_steps,
                                                                                  loss_cache, step_cache, blocks_cache,
                                                                                  cache_stride, cache_offset, resampled,
-                                                                                 resync_every);
+                                                                                 resync_every, c->step_tile_off);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;

@@ -52,6 +52,41 @@ def box_muller(r):
     return rad * np.cos(np.pi * ang), rad * np.sin(np.pi * ang)
 
 
+def hermitian_noise(key, it, h, w):
+    """Full-plane noise arrays (A, B) equivalent to the kernel's direct draw of the Hermitian half plane (step.cu,
+    synth_field step 1): Re(ifft2((A + iB) sqrt(S))) equals the kernel's field up to rounding.
+
+    Kernel: for kx in (0, w/2): X_h(ky,kx) = sqrt(S) (z0 + i z1)/sqrt(2) with (z0,z1) = BoxMuller(Philox(ky*w+kx));
+    columns kx in {0, w/2}: same for 0 < ky < h/2 and X_h(h-ky) = conj(X_h(ky)); the four self-conjugate points are real,
+    sqrt(S) z0.  Reference algebra: X_h(k) = sqrt(S)/2 ((A_k + A_-k) + i (B_k - B_-k)).
+    """
+    lo, hi = it & 0xFFFFFFFF, (it >> 32) & 0xFFFFFFFF
+    e = np.arange(h * w, dtype=np.uint32)
+    z0, z1 = box_muller(philox4x32(key, e, lo, hi, STREAM_NOISE))
+    z0, z1 = z0.reshape(h, w), z1.reshape(h, w)
+    A = np.zeros((h, w))
+    B = np.zeros((h, w))
+    n2 = w // 2
+    r2 = np.sqrt(0.5)
+    for ky in range(h):
+        nky = (h - ky) % h
+        for kx in range(n2 + 1):
+            nkx = (w - kx) % w
+            self_y = ky in (0, h // 2)
+            if kx in (0, n2):
+                if self_y:
+                    A[ky, kx] = z0[ky, kx]
+                elif ky < h // 2:
+                    p, q = z0[ky, kx] * r2, z1[ky, kx] * r2
+                    A[ky, kx] = A[nky, kx] = p
+                    B[ky, kx], B[nky, kx] = q, -q
+            else:
+                p, q = z0[ky, kx] * r2, z1[ky, kx] * r2
+                A[ky, kx] = A[nky, nkx] = p
+                B[ky, kx], B[nky, nkx] = q, -q
+    return A, B
+
+
 def step_draws(key, it, n_pairs, pairs, fm, H, W, centre_cells):
     """All random inputs of iteration `it` of one chain, in oracle terms."""
     lo, hi = it & 0xFFFFFFFF, (it >> 32) & 0xFFFFFFFF
@@ -70,7 +105,7 @@ def step_draws(key, it, n_pairs, pairs, fm, H, W, centre_cells):
         range_y = f64(fm["range_min_y"]) + (f64(fm["range_max_y"]) - f64(fm["range_min_y"])) * u(r2[0], r2[1])
     bw, bh = int(pairs[0, pick]), int(pairs[1, pick])
     e = np.arange(bh * bw, dtype=np.uint32)
-    z_re, z_im = box_muller(philox4x32(key, e, lo, hi, STREAM_NOISE))
+    z_re, z_im = hermitian_noise(key, it, bh, bw)
     z_nug, _ = box_muller(philox4x32(key, e, lo, hi, STREAM_NUGGET))
     c0 = [int(x) for x in philox4x32(key, 0, lo, hi, STREAM_CHAIN)]
     c1 = [int(x) for x in philox4x32(key, 1, lo, hi, STREAM_CHAIN)]
