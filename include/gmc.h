@@ -149,6 +149,16 @@ GMC_API int64_t gmc_launch_count(const gmc_ctx* ctx);
 /* Dynamic shared memory (bytes) and threads per CTA of the fused step kernel for the current block table. */
 GMC_API int gmc_step_kernel_info(const gmc_ctx* ctx, int* smem_bytes, int* threads, int* ctas_per_sm);
 
+/* Debug: per-phase SM-cycle accounting of the fused step kernel (thread 0 of every CTA, summed over CTAs and steps).
+ * enable != 0 allocates/zeroes the counters, 0 releases them; cycles_out (host, 8 x int64, may be NULL) receives the
+ * counters accumulated so far: 0 scalars+prefetch, 1 spectrum fill, 2 column DFT, 3 row recombination, 4 row DFT,
+ * 5 candidate tile, 6 block residual+loss+decision, 7 write-back. */
+GMC_API int gmc_debug_phase_timing(gmc_ctx* ctx, int enable, int64_t* cycles_out);
+
+/* Debug/test: compares the stencil kernels' division-by-constant (reciprocal + FMA residual correction) with the
+ * correctly rounded division for n dividends x (dev) and one divisor; *mismatches_out = number of differing bit patterns. */
+GMC_API int gmc_debug_div_check(gmc_ctx* ctx, const double* x, int64_t n, double divisor, int64_t* mismatches_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -508,8 +508,13 @@ class ChainBatch:
     def close(self):
         self.bed = self.mcres = self.resampled = self._cache = None
 
+    def _loss_now(self):
+        # tensor / tensor is an IEEE division on the device (tensor / python scalar multiplies by a reciprocal)
+        den = self.torch.full_like(self.ssq, 2 * self.chain.sigma_mc ** 2)
+        return self.ssq / den
+
     def loss(self):
-        return (self.ssq / (2 * self.chain.sigma_mc ** 2)).cpu().numpy()
+        return self._loss_now().cpu().numpy()
 
     def beds(self):
         return self.bed.cpu().numpy()
@@ -549,7 +554,7 @@ class ChainBatch:
         torch = self.torch
         n = n_steps + 1
         lc, st, bl = self._device_caches(n)
-        lc[:, 0] = self.ssq / (2 * self.chain.sigma_mc ** 2)
+        lc[:, 0] = self._loss_now()
         st[:, 0] = 0
         bl[:, 0] = -1
         self.ctx.run(self.bed, self.mcres, self.ssq, self.seeds, self.iteration, n_steps, lc, st, bl, 1, self.resampled,

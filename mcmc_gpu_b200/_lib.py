@@ -49,6 +49,8 @@ PROTOTYPES = {
     "gmc_allreduce_moments": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "gmc_launch_count": (_i64, [_c_p]),
     "gmc_step_kernel_info": (C.c_int, [_c_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gmc_debug_phase_timing": (C.c_int, [_c_p, C.c_int, _c_p]),
+    "gmc_debug_div_check": (C.c_int, [_c_p, _c_p, _i64, _f64, C.POINTER(_i64)]),
 }
 
 _lib = None
@@ -231,6 +233,18 @@ class Context:
 
     def launch_count(self) -> int:
         return int(self.lib.gmc_launch_count(self._h))
+
+    def phase_timing(self, enable=True, read=False):
+        """Debug: enable/zero or read the per-phase cycle counters of the fused step kernel."""
+        out = np.zeros(8, dtype=np.int64) if read else None
+        check(self.lib.gmc_debug_phase_timing(self._h, int(bool(enable)), _ptr(out)))
+        return out
+
+    def div_check(self, x, divisor) -> int:
+        """Debug: number of elements of the CUDA tensor x for which x/divisor by reciprocal+FMA differs from IEEE division."""
+        n = _i64(0)
+        check(self.lib.gmc_debug_div_check(self._h, _ptr(x), x.numel(), float(divisor), C.byref(n)))
+        return int(n.value)
 
     def step_kernel_info(self):
         a, b, c = C.c_int(), C.c_int(), C.c_int()

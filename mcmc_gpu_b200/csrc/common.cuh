@@ -13,7 +13,13 @@
 
 #define GMC_MAX_RADIX 64       // largest prime factor of a block edge handled by the smem FFT (generic stage)
 #define GMC_MAX_FACTORS 12
+#ifndef GMC_STEP_THREADS
 #define GMC_STEP_THREADS 256
+#endif
+#ifndef GMC_STEP_MIN_CTAS
+#define GMC_STEP_MIN_CTAS 2
+#endif
+#define GMC_N_PHASES 8
 
 // ---------------------------------------------------------------------------------------------------------------
 // host: errors
@@ -120,6 +126,7 @@ struct gmc_ctx {
     int step_tile_off;     // offset (in doubles) of the candidate tile inside the step kernel's dynamic shared memory
     int step_ctas_per_sm;
     int64_t launches;
+    long long* d_phase;    // optional per-phase cycle counters of run_kernel (debug)
 };
 
 #define FLAG_GATE 1

@@ -1,86 +1,316 @@
-// residual.cu — K2/K3: batched full-grid mass-conservation residual and masked loss.
+// residual.cu — K2/K3: batched full-grid mass-conservation residual and masked loss (the "stencil" of the metric).
 //
 // Reference semantics (Topography.py:592-600, MCMC.py:1041):
 //   thick = surf - bed;  dx = np.gradient(velx*thick, res, axis=1);  dy = np.gradient(vely*thick, res, axis=0)
 //   out = ((dx + dy) + dhdt) - smb;   loss = nansum(out[mask==1]^2) / (2 sigma^2)
 // np.gradient (uniform spacing, edge_order=1): interior (f[i+1]-f[i-1])/(2.*h), first/last (f[1]-f[0])/h.
-// All arithmetic is rounded per operation (no FMA contraction, true division) so the result is bit-identical
-// to numpy.  The loss is summed in a fixed order (deterministic), which differs from numpy's pairwise order only
-// by rounding (<= 1e-12 relative; the contract is 1e-9).
+// Every operation is rounded separately (no FMA contraction) and the divisions are correctly rounded, so the
+// residual is bit-identical to numpy.  The loss is summed in a fixed order (deterministic); it differs from numpy's
+// pairwise order by rounding only (<= 1e-12 relative; the contract is 1e-9).
+//
+// Design (HBM-bound: 8 B read + 8 B written per cell per chain, everything else must stay on chip):
+//   * a CTA owns a 16 x 64 cell tile and loops over a group of chains; the five chain-independent fields of the tile
+//     (+halo) are staged ONCE in shared memory, so per chain only the bed is read from and the residual written to HBM;
+//   * a warp owns RS_RW rows x 64 columns, a lane 2 adjacent columns: 16-byte accesses; x-neighbours come from warp
+//     shuffles, y-neighbours from the lane's own registers (the warp fetches its own halo rows);
+//   * the bed of the next chains streams in through a per-warp cp.async ring in shared memory (RS_STAGES-1 chains in
+//     flight per warp): bytes in flight, not registers or warps, are what HBM latency has to be covered with;
+//   * x/(2 res) uses the precomputed reciprocal with one FMA residual correction (correctly rounded, see div_const).
 #include "common.cuh"
 
-#define RES_TX 32
-#define RES_TY 8
-#define RES_ROWS_PER_THREAD 4   // each CTA covers RES_TY*RES_ROWS_PER_THREAD rows x RES_TX*2 columns
-#define RES_TILE_H (RES_TY * RES_ROWS_PER_THREAD)
-#define RES_TILE_W (RES_TX * 2)
+#ifndef RS_RW
+#define RS_RW 2                       // rows per warp (even)
+#endif
+#ifndef RS_WARPS
+#define RS_WARPS 4                    // warps per CTA
+#endif
+#define RS_TH (RS_RW * RS_WARPS)      // tile height 16
+#define RS_TW 64                      // tile width (2 columns per lane)
+#define RS_PITCH (RS_TW + 4)          // smem row pitch in doubles: [pad, haloL, 64 cells, haloR, pad] -> cells 16 B aligned
+#define RS_THREADS (RS_WARPS * 32)
+#ifndef RS_STAGES
+#define RS_STAGES 3                   // cp.async ring depth per warp
+#endif
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 4                 // 4 CTAs/SM: 46.7 KB of staged statics each, <= 128 registers per thread
+#endif
 
-__device__ __forceinline__ double cell_fx(const GmcDev& d, const double* __restrict__ bed, int64_t idx) {
-    return mul_rn(__ldg(d.velx + idx), sub_rn(__ldg(d.surf + idx), bed[idx]));
-}
-__device__ __forceinline__ double cell_fy(const GmcDev& d, const double* __restrict__ bed, int64_t idx) {
-    return mul_rn(__ldg(d.vely + idx), sub_rn(__ldg(d.surf + idx), bed[idx]));
-}
-
-// residual of one cell from global memory (used by the v1 kernel; the step kernel has its own smem version)
-__device__ __forceinline__ double cell_residual(const GmcDev& d, const double* __restrict__ bed, int i, int j) {
-    const int H = d.H, W = d.W;
-    const int64_t row = (int64_t)i * W;
-    double dx, dy;
-    if (j == 0)
-        dx = div_rn(sub_rn(cell_fx(d, bed, row + 1), cell_fx(d, bed, row)), d.res);
-    else if (j == W - 1)
-        dx = div_rn(sub_rn(cell_fx(d, bed, row + W - 1), cell_fx(d, bed, row + W - 2)), d.res);
-    else
-        dx = div_rn(sub_rn(cell_fx(d, bed, row + j + 1), cell_fx(d, bed, row + j - 1)), d.two_res);
-    if (i == 0)
-        dy = div_rn(sub_rn(cell_fy(d, bed, (int64_t)W + j), cell_fy(d, bed, j)), d.res);
-    else if (i == H - 1)
-        dy = div_rn(sub_rn(cell_fy(d, bed, row + j), cell_fy(d, bed, row - W + j)), d.res);
-    else
-        dy = div_rn(sub_rn(cell_fy(d, bed, row + W + j), cell_fy(d, bed, row - W + j)), d.two_res);
-    return sub_rn(add_rn(add_rn(dx, dy), __ldg(d.dhdt + row + j)), __ldg(d.smb + row + j));
+// x / d for a loop-invariant d with r = RN(1/d): q = RN(x r), rem = x - d q (exact in one FMA), q' = RN(q + rem r).
+// This is the final correction step of the IEEE division routine; with a correctly rounded reciprocal it returns
+// RN(x/d) whenever no intermediate over/underflows, which the magnitude guard ensures (else the true division runs).
+// tests/test_gpu_residual.py checks it against __ddiv_rn on random and adversarial operands.
+__device__ __noinline__ double div_slow(double x, double d) { return div_rn(x, d); }
+__device__ __forceinline__ double div_const(double x, double d, double r) {
+    const double q = mul_rn(x, r);
+    const double aq = fabs(q);
+    if (aq > 1e-280 && aq < 1e280) return fma(fma(-d, q, x), r, q);
+    return div_slow(x, d);       // zero, subnormal, huge, inf, nan: rare, kept out of line
 }
 
-template <bool WRITE_RES, bool DO_LOSS>
-__global__ void __launch_bounds__(RES_TX* RES_TY)
-    residual_kernel(GmcDev d, const double* __restrict__ bed_all, double* __restrict__ res_all,
-                    double* __restrict__ partials, int n_tiles) {
-    __shared__ double scratch[33];
-    const int c = blockIdx.z;
-    const int64_t plane = (int64_t)d.H * d.W;
-    const double* bed = bed_all + c * plane;
-    const int j0 = (blockIdx.x * RES_TX + threadIdx.x) * 2;
-    const int i0 = blockIdx.y * RES_TILE_H + threadIdx.y * RES_ROWS_PER_THREAD;
+struct ResSmem {
+    double surf[RS_TH + 2][RS_PITCH];
+    double velx[RS_TH][RS_PITCH];
+    double vely[RS_TH + 2][RS_PITCH];
+    double dhdt[RS_TH][RS_PITCH];
+    double smb[RS_TH][RS_PITCH];
+    uint8_t mc[RS_TH][RS_TW];
+    double ring[RS_STAGES][RS_WARPS][RS_RW + 2][RS_PITCH];   // per-warp landing zone of the streamed bed rows
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Loop-invariant geometry of one lane.
+struct LaneGeom {
+    int W, H, i0, lane, wr0, sc, hsc;
+    unsigned rowmask;      // bit k: grid row i0-1+k exists
+    bool v0, v1, hval;
+    bool xl_edge, xr0_edge, xr1_edge;
+    int k_top, k_bot;      // k of grid row 0 / H-1 inside this warp's rows, or -1
+    int64_t hoff;          // offset of the halo column relative to the lane's first column
+};
+
+// INTERIOR: the warp's rows and all 64 columns (+halo) lie strictly inside the grid: no predicates, no edge rules.
+// Every lane copies exactly the cells it will read back itself, so cp.async.wait_group alone orders the ring.
+template <bool VEC, bool INTERIOR>
+__device__ __forceinline__ void fetch_bed(const LaneGeom& g, const double* __restrict__ p, double (*slot)[RS_PITCH]) {
+    // p -> (row i0-1, column c0) of the chain's bed; slot -> this warp's [RS_RW+2][RS_PITCH] ring stage
+#pragma unroll
+    for (int k = 0; k < RS_RW + 2; ++k) {
+        if (INTERIOR || (((g.rowmask >> k) & 1u) && g.v0)) {
+            const double* q = p + (int64_t)k * g.W;
+            if (VEC) cp_async16(&slot[k][g.sc], q);
+            else {
+                cp_async8(&slot[k][g.sc], q);
+                if (g.v1) cp_async8(&slot[k][g.sc + 1], q + 1);
+            }
+        }
+    }
+    if (INTERIOR ? (g.lane == 0 || g.lane == 31) : g.hval) {
+#pragma unroll
+        for (int k = 1; k <= RS_RW; ++k)
+            if (INTERIOR || ((g.rowmask >> k) & 1u)) cp_async8(&slot[k][g.hsc], p + (int64_t)k * g.W + g.hoff);
+    }
+}
+
+// true when |x| lies in [2^-930, 2^930]: the FMA-corrected quotient is then free of over/underflow (see div_const)
+__device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
+
+template <bool WRITE_RES, bool DO_LOSS, bool VEC, bool INTERIOR>
+__device__ __forceinline__ void compute_rows(const GmcDev& d, const ResSmem& S, const LaneGeom& g,
+                                             const double (*bed)[RS_PITCH], double* __restrict__ out,
+                                             double* __restrict__ partial, double r_res, double r_two_res) {
+    // ---- fluxes: fy for rows -1..RS_RW, fx for rows 0..RS_RW-1 --------------------------------------------------
+    double fy0[RS_RW + 2], fy1[RS_RW + 2], fx0[RS_RW], fx1[RS_RW], fxh[RS_RW];
+#pragma unroll
+    for (int k = 0; k < RS_RW + 2; ++k) {
+        const double2 sf = *reinterpret_cast<const double2*>(&S.surf[g.wr0 + k][g.sc]);
+        const double2 vy = *reinterpret_cast<const double2*>(&S.vely[g.wr0 + k][g.sc]);
+        const double2 bd = *reinterpret_cast<const double2*>(&bed[k][g.sc]);
+        const double t0 = sub_rn(sf.x, bd.x), t1 = sub_rn(sf.y, bd.y);
+        fy0[k] = mul_rn(vy.x, t0);
+        fy1[k] = mul_rn(vy.y, t1);
+        if (k >= 1 && k <= RS_RW) {
+            const double2 vx = *reinterpret_cast<const double2*>(&S.velx[g.wr0 + k - 1][g.sc]);
+            fx0[k - 1] = mul_rn(vx.x, t0);
+            fx1[k - 1] = mul_rn(vx.y, t1);
+            fxh[k - 1] = mul_rn(S.velx[g.wr0 + k - 1][g.hsc], sub_rn(S.surf[g.wr0 + k][g.hsc], bed[k][g.hsc]));
+        }
+    }
+    // np.gradient's one-sided first/last rows as data: duplicating the edge row into the missing neighbour turns the
+    // central difference into (f[1]-f[0]) resp. (f[n-1]-f[n-2]); only the divisor changes (res instead of 2 res).
+    if (!INTERIOR) {
+#pragma unroll
+        for (int k = 0; k < RS_RW; ++k) {
+            if (k == g.k_top) { fy0[k] = fy0[k + 1]; fy1[k] = fy1[k + 1]; }
+            if (k == g.k_bot) { fy0[k + 2] = fy0[k + 1]; fy1[k + 2] = fy1[k + 1]; }
+        }
+    }
+    // x-neighbours of every row first (straight-line code: the shuffles of all rows overlap)
+    double fl[RS_RW], fr[RS_RW];
+#pragma unroll
+    for (int k = 0; k < RS_RW; ++k) {
+        // left of column c0 is lane-1's second column, right of column c0+1 is lane+1's first
+        fl[k] = __shfl_up_sync(0xffffffffu, fx1[k], 1);
+        fr[k] = __shfl_down_sync(0xffffffffu, fx0[k], 1);
+        if (g.lane == 0) fl[k] = fxh[k];
+        if (g.lane == 31) fr[k] = fxh[k];
+    }
     double acc = 0.0;
+    // two rows at a time: 8 independent quotient chains in flight, one range check and one (cold) branch per pair
 #pragma unroll
-    for (int r = 0; r < RES_ROWS_PER_THREAD; ++r) {
-        const int i = i0 + r;
-        if (i >= d.H) break;
+    for (int kk = 0; kk < RS_RW; kk += 2) {
+        double num[2][4], den[2][4], rdn[2][4], quo[2][4];
+        int lo = 0x7fffffff, hi = 0;
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const int j = j0 + q;
-            if (j >= d.W) break;
-            const double v = cell_residual(d, bed, i, j);
-            const int64_t idx = (int64_t)i * d.W + j;
-            if (WRITE_RES) res_all[c * plane + idx] = v;
-            if (DO_LOSS) {
-                if ((__ldg(d.flags + idx) & FLAG_MC) && v == v) acc = add_rn(acc, mul_rn(v, v));
+        for (int u = 0; u < 2; ++u) {
+            const int k = kk + u;
+            double a0 = fx1[k], l = fl[k], rr = fr[k];
+            double deny = d.two_res, rdeny = r_two_res, den0 = d.two_res, rden0 = r_two_res, den1 = d.two_res, rden1 = r_two_res;
+            if (!INTERIOR) {
+                if (g.xl_edge) l = fx0[k];                        // column 0:   (f[1]   - f[0]  )/res
+                if (g.xr1_edge) rr = fx1[k];                      // column W-1: (f[W-1] - f[W-2])/res (second column)
+                if (g.xr0_edge) a0 = fx0[k];                      // column W-1 as first column (odd W)
+                if ((k == g.k_top) || (k == g.k_bot)) { deny = d.res; rdeny = r_res; }
+                if (g.xl_edge || g.xr0_edge) { den0 = d.res; rden0 = r_res; }
+                if (g.xr1_edge) { den1 = d.res; rden1 = r_res; }
+            }
+            num[u][0] = sub_rn(a0, l);
+            num[u][1] = sub_rn(rr, fx0[k]);
+            num[u][2] = sub_rn(fy0[k + 2], fy0[k]);
+            num[u][3] = sub_rn(fy1[k + 2], fy1[k]);
+            den[u][0] = den0; rdn[u][0] = rden0;
+            den[u][1] = den1; rdn[u][1] = rden1;
+            den[u][2] = den[u][3] = deny;
+            rdn[u][2] = rdn[u][3] = rdeny;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                // x / den by reciprocal + one FMA residual correction (see div_const)
+                const double q = mul_rn(num[u][j], rdn[u][j]);
+                // the correction never changes the sign; copysign also keeps -0 (0/den) exact
+                quo[u][j] = copysign(fma(fma(-den[u][j], q, num[u][j]), rdn[u][j], q), q);
+                int e = hi_abs(q);
+                if ((e | __double2loint(q)) == 0) e = 0x3ff00000;            // exact zero: the fast path is exact
+                if (!INTERIOR && !(((g.rowmask >> (k + 1)) & 1u) && g.v0)) e = 0x3ff00000;   // padding lane/row: ignored
+                lo = min(lo, e);
+                hi = max(hi, e);
+            }
+        }
+        if (lo < 0x05d00000 || hi > 0x7a100000) {                 // zero, subnormal, huge, inf or nan somewhere: exact path
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) quo[u][j] = div_slow(num[u][j], den[u][j]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int k = kk + u;
+            const double2 dh = *reinterpret_cast<const double2*>(&S.dhdt[g.wr0 + k][g.sc]);
+            const double2 sm = *reinterpret_cast<const double2*>(&S.smb[g.wr0 + k][g.sc]);
+            const double r0 = sub_rn(add_rn(add_rn(quo[u][0], quo[u][2]), dh.x), sm.x);
+            const double r1 = sub_rn(add_rn(add_rn(quo[u][1], quo[u][3]), dh.y), sm.y);
+            if (INTERIOR || (((g.rowmask >> (k + 1)) & 1u) && g.v0)) {
+                if (WRITE_RES) {
+                    double* q = out + (int64_t)(k + 1) * g.W;
+                    if (VEC) __stcs(reinterpret_cast<double2*>(q), make_double2(r0, r1));
+                    else {
+                        __stcs(q, r0);
+                        if (INTERIOR || g.v1) __stcs(q + 1, r1);
+                    }
+                }
+                if (DO_LOSS) {
+                    const uchar2 m = *reinterpret_cast<const uchar2*>(&S.mc[g.wr0 + k][2 * g.lane]);
+                    if (m.x && r0 == r0) acc = add_rn(acc, mul_rn(r0, r0));
+                    if ((INTERIOR || g.v1) && m.y && r1 == r1) acc = add_rn(acc, mul_rn(r1, r1));
+                }
             }
         }
     }
     if (DO_LOSS) {
-        const int tid = threadIdx.y * RES_TX + threadIdx.x;
-        // block_sum uses threadIdx.x only; flatten
-        double v = warp_sum(acc);
-        if ((tid & 31) == 0) scratch[tid >> 5] = v;
-        __syncthreads();
-        if (tid < 32) {
-            double t = (tid < (RES_TX * RES_TY) / 32) ? scratch[tid] : 0.0;
-            t = warp_sum(t);
-            if (tid == 0) partials[(int64_t)c * n_tiles + blockIdx.y * gridDim.x + blockIdx.x] = t;
+        acc = warp_sum(acc);
+        if (g.lane == 0) *partial = acc;
+    }
+}
+
+template <bool WRITE_RES, bool DO_LOSS, bool VEC, bool INTERIOR>
+__device__ __forceinline__ void chain_loop(const GmcDev& d, ResSmem& S, const LaneGeom& g, int warp, const double* __restrict__ pb,
+                                           double* __restrict__ po, double* __restrict__ pp, int64_t plane, int n_tiles, int C,
+                                           double r_res, double r_two_res) {
+    const int G = gridDim.z;
+    const int64_t cstride = (int64_t)G * plane, pstride = (int64_t)G * n_tiles;
+    const int n_iter = (C - (int)blockIdx.z + G - 1) / G;          // chains blockIdx.z, +G, +2G, ...
+    // prologue: RS_STAGES-1 chains in flight (empty groups keep the group count uniform)
+#pragma unroll
+    for (int s = 0; s < RS_STAGES - 1; ++s) {
+        if (s < n_iter) fetch_bed<VEC, INTERIOR>(g, pb + s * cstride, S.ring[s][warp]);
+        cp_async_commit();
+    }
+    int stage = 0;
+    for (int it = 0; it < n_iter; ++it) {
+        const int nxt = it + RS_STAGES - 1;
+        int ns = stage + RS_STAGES - 1;
+        if (ns >= RS_STAGES) ns -= RS_STAGES;
+        if (nxt < n_iter) fetch_bed<VEC, INTERIOR>(g, pb + (int64_t)nxt * cstride, S.ring[ns][warp]);
+        cp_async_commit();
+        cp_async_wait<RS_STAGES - 1>();                            // this lane's copies of chain `it` have landed
+        compute_rows<WRITE_RES, DO_LOSS, VEC, INTERIOR>(d, S, g, S.ring[stage][warp], po, pp, r_res, r_two_res);
+        if (WRITE_RES) po += cstride;
+        pp += pstride;
+        if (++stage == RS_STAGES) stage = 0;
+    }
+    cp_async_wait<0>();
+}
+
+template <bool WRITE_RES, bool DO_LOSS, bool VEC>
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
+    residual_kernel(GmcDev d, const double* __restrict__ bed_all, double* __restrict__ res_all,
+                    double* __restrict__ partials, int n_tiles, int C, double r_res, double r_two_res) {
+    extern __shared__ __align__(16) unsigned char rs_raw[];
+    ResSmem& S = *reinterpret_cast<ResSmem*>(rs_raw);
+    const int H = d.H, W = d.W;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tx0 = blockIdx.x * RS_TW, ty0 = blockIdx.y * RS_TH;
+    const int64_t plane = (int64_t)H * W;
+
+    // ---- stage the chain-independent fields of this tile (+ one-cell halo) --------------------------------
+    for (int t = tid; t < (RS_TH + 2) * (RS_TW + 2); t += RS_THREADS) {
+        const int rr = t / (RS_TW + 2), cc = t - rr * (RS_TW + 2);      // rr in [0,18): row ty0-1+rr; cc in [0,66): col tx0-1+cc
+        const int i = ty0 - 1 + rr, j = tx0 - 1 + cc;
+        const bool in = i >= 0 && i < H && j >= 0 && j < W;
+        const int64_t idx = (int64_t)i * W + j;
+        S.surf[rr][cc + 1] = in ? __ldg(d.surf + idx) : 0.0;
+        S.vely[rr][cc + 1] = in ? __ldg(d.vely + idx) : 0.0;
+        if (rr >= 1 && rr <= RS_TH) {
+            S.velx[rr - 1][cc + 1] = in ? __ldg(d.velx + idx) : 0.0;
+            S.dhdt[rr - 1][cc + 1] = in ? __ldg(d.dhdt + idx) : 0.0;
+            S.smb[rr - 1][cc + 1] = in ? __ldg(d.smb + idx) : 0.0;
+            if (cc >= 1 && cc <= RS_TW) S.mc[rr - 1][cc - 1] = in ? (__ldg(d.flags + idx) & FLAG_MC) : 0;
         }
     }
+    for (int t = tid; t < RS_STAGES * RS_WARPS * (RS_RW + 2) * RS_PITCH; t += RS_THREADS) (&S.ring[0][0][0][0])[t] = 0.0;
+    __syncthreads();
+
+    LaneGeom g;
+    g.W = W;
+    g.H = H;
+    g.lane = lane;
+    g.wr0 = warp * RS_RW;                         // first tile row of this warp
+    g.i0 = ty0 + g.wr0;                           // first grid row
+    if (g.i0 >= H) return;                        // warp-uniform; no block-wide barriers below
+    const int c0 = tx0 + 2 * lane;                // first grid column of this lane
+    g.sc = 2 * lane + 2;                          // smem column of c0 (16 B aligned)
+    g.v0 = c0 < W;
+    g.v1 = c0 + 1 < W;
+    const int hcol = (lane == 0) ? c0 - 1 : c0 + 2;          // lane 0: left of the tile, lane 31: right of it
+    g.hval = (lane == 0 && hcol >= 0) || (lane == 31 && hcol < W);
+    g.hsc = (lane == 0) ? g.sc - 1 : g.sc + 2;
+    g.hoff = hcol - c0;
+    g.xl_edge = (c0 == 0);
+    g.xr0_edge = (c0 == W - 1);
+    g.xr1_edge = (c0 + 1 == W - 1);
+    g.rowmask = 0;
+    for (int k = 0; k < RS_RW + 2; ++k)
+        if (g.i0 - 1 + k >= 0 && g.i0 - 1 + k < H) g.rowmask |= 1u << k;
+    g.k_top = (g.i0 == 0) ? 0 : -1;
+    g.k_bot = (H - 1 >= g.i0 && H - 1 < g.i0 + RS_RW) ? H - 1 - g.i0 : -1;
+    const int tile_id = (blockIdx.y * RS_WARPS + warp) * gridDim.x + blockIdx.x;
+
+    // chains c = blockIdx.z, +G, +2G, ...: two register sets ping-pong so the next chain's bed is always in flight
+    const int64_t lane_off = (int64_t)(g.i0 - 1) * W + c0;
+    const double* pb = bed_all + (int64_t)blockIdx.z * plane + lane_off;
+    double* po = WRITE_RES ? res_all + (int64_t)blockIdx.z * plane + lane_off : nullptr;
+    double* pp = partials + (int64_t)blockIdx.z * n_tiles + tile_id;
+    const bool interior = tx0 > 0 && tx0 + RS_TW < W && g.i0 > 0 && g.i0 + RS_RW < H;   // warp-uniform
+    if ((int)blockIdx.z >= C) return;
+    if (interior) chain_loop<WRITE_RES, DO_LOSS, VEC, true>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res);
+    else chain_loop<WRITE_RES, DO_LOSS, VEC, false>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res);
 }
 
 // masked nansum of squares of given residuals: one CTA per (chunk, chain)
@@ -96,7 +326,7 @@ __global__ void __launch_bounds__(LOSS_THREADS)
     const int64_t hi = (lo + chunk < plane) ? lo + chunk : plane;
     double acc = 0.0;
     for (int64_t k = lo + threadIdx.x; k < hi; k += LOSS_THREADS) {
-        const double v = res[k];
+        const double v = __ldcs(res + k);
         if ((__ldg(d.flags + k) & FLAG_MC) && v == v) acc = add_rn(acc, mul_rn(v, v));
     }
     const double t = block_sum<LOSS_THREADS>(acc, scratch);
@@ -118,12 +348,24 @@ __global__ void finalize_loss_kernel(const double* __restrict__ partials, int n_
     }
 }
 
+// debug/test hook: div_const vs the true division on caller-provided dividends
+__global__ void div_check_kernel(const double* __restrict__ x, int64_t n, double dd, double r, unsigned long long* mismatches) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double a = div_const(x[k], dd, r), b = div_rn(x[k], dd);
+    if (__double_as_longlong(a) != __double_as_longlong(b) && !(a != a && b != b)) atomicAdd(mismatches, 1ull);
+}
+
+static int tiles_x(const gmc_ctx* c) { return (c->W + RS_TW - 1) / RS_TW; }
+static int tiles_y(const gmc_ctx* c) { return (c->H + RS_TH - 1) / RS_TH; }
+
 static int ensure_partials(gmc_ctx* c) {
-    const int tiles = ((c->W + RES_TILE_W - 1) / RES_TILE_W) * ((c->H + RES_TILE_H - 1) / RES_TILE_H);
+    const int tiles = tiles_x(c) * tiles_y(c) * RS_WARPS;
     if (!c->d_partials || c->n_tiles != tiles) {
         cudaFree(c->d_partials);
         c->d_partials = nullptr;
         GMC_CUDA(cudaMalloc(&c->d_partials, (size_t)c->max_chains * tiles * sizeof(double)));
+        GMC_CUDA(cudaMemset(c->d_partials, 0, (size_t)c->max_chains * tiles * sizeof(double)));
         c->n_tiles = tiles;
     }
     return GMC_OK;
@@ -138,26 +380,35 @@ static int check_common(gmc_ctx* c, const void* p, int C, const char* who) {
     return GMC_OK;
 }
 
+template <bool WR, bool LS>
+static void launch_variant(gmc_ctx* c, dim3 grid, cudaStream_t st, const double* bed, double* res, int C, bool vec) {
+    const double r_res = 1.0 / c->dev.res, r_two = 1.0 / c->dev.two_res;
+    const size_t smem = sizeof(ResSmem);
+    if (vec) {
+        cudaFuncSetAttribute(residual_kernel<WR, LS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        residual_kernel<WR, LS, true><<<grid, RS_THREADS, smem, st>>>(c->dev, bed, res, c->d_partials, c->n_tiles, C, r_res, r_two);
+    } else {
+        cudaFuncSetAttribute(residual_kernel<WR, LS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        residual_kernel<WR, LS, false><<<grid, RS_THREADS, smem, st>>>(c->dev, bed, res, c->d_partials, c->n_tiles, C, r_res, r_two);
+    }
+}
+
 static int launch_residual(gmc_ctx* c, const double* bed, double* res_out, double* loss_out, double* ssq_out, int C,
                            bool do_loss, cudaStream_t st) {
     int rc = ensure_partials(c);
     if (rc) return rc;
-    const dim3 block(RES_TX, RES_TY);
-    const int tx = (c->W + RES_TILE_W - 1) / RES_TILE_W, ty = (c->H + RES_TILE_H - 1) / RES_TILE_H;
-    for (int c0 = 0; c0 < C; c0 += 65535) {
-        const int cn = (C - c0 < 65535) ? C - c0 : 65535;
-        const dim3 grid(tx, ty, cn);
-        const double* b = bed + (size_t)c0 * c->H * c->W;
-        double* r = res_out ? res_out + (size_t)c0 * c->H * c->W : nullptr;
-        double* p = c->d_partials + (size_t)c0 * c->n_tiles;
-        if (res_out && do_loss)
-            residual_kernel<true, true><<<grid, block, 0, st>>>(c->dev, b, r, p, c->n_tiles);
-        else if (res_out)
-            residual_kernel<true, false><<<grid, block, 0, st>>>(c->dev, b, r, p, c->n_tiles);
-        else
-            residual_kernel<false, true><<<grid, block, 0, st>>>(c->dev, b, r, p, c->n_tiles);
-        c->launches++;
-    }
+    const int tx = tiles_x(c), ty = tiles_y(c);
+    // chain groups: enough CTAs for ~8 per SM, but keep >= 8 chains per CTA to amortise the staged statics
+    int groups = (24 * c->sm_count + tx * ty - 1) / (tx * ty);     // ~6 waves of 4 CTAs/SM: small tail
+    groups = std::max(1, std::min(groups, std::max(1, C / 8)));
+    groups = std::min(groups, 65535);
+    const dim3 grid(tx, ty, groups);
+    // 16-byte accesses need even W and 16 B aligned bases
+    const bool vec = (c->W % 2 == 0) && ((uintptr_t)bed % 16 == 0) && (!res_out || (uintptr_t)res_out % 16 == 0);
+    if (res_out && do_loss) launch_variant<true, true>(c, grid, st, bed, res_out, C, vec);
+    else if (res_out) launch_variant<true, false>(c, grid, st, bed, res_out, C, vec);
+    else launch_variant<false, true>(c, grid, st, bed, res_out, C, vec);
+    c->launches++;
     if (do_loss) {
         finalize_loss_kernel<<<(C + 7) / 8, 256, 0, st>>>(c->d_partials, c->n_tiles, c->dev.two_sigma2, loss_out, ssq_out, C);
         c->launches++;
@@ -188,14 +439,31 @@ extern "C" int gmc_loss(gmc_ctx* c, const double* res, double* loss_out, double*
     rc = ensure_partials(c);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    // chunks of >= 16 K cells per CTA (each thread streams >= 64 cells), at most as many as there are partial slots
+    const int64_t plane = (int64_t)c->H * c->W;
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(c->n_tiles, plane / 16384));
     for (int c0 = 0; c0 < C; c0 += 65535) {
         const int cn = (C - c0 < 65535) ? C - c0 : 65535;
-        loss_kernel<<<dim3(c->n_tiles, cn), LOSS_THREADS, 0, st>>>(c->dev, res + (size_t)c0 * c->H * c->W,
-                                                                  c->d_partials + (size_t)c0 * c->n_tiles, c->n_tiles);
+        loss_kernel<<<dim3(chunks, cn), LOSS_THREADS, 0, st>>>(c->dev, res + (size_t)c0 * c->H * c->W,
+                                                              c->d_partials + (size_t)c0 * chunks, chunks);
         c->launches++;
     }
-    finalize_loss_kernel<<<(C + 7) / 8, 256, 0, st>>>(c->d_partials, c->n_tiles, c->dev.two_sigma2, loss_out, ssq_out, C);
+    finalize_loss_kernel<<<(C + 7) / 8, 256, 0, st>>>(c->d_partials, chunks, c->dev.two_sigma2, loss_out, ssq_out, C);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+extern "C" int gmc_debug_div_check(gmc_ctx* c, const double* x, int64_t n, double divisor, int64_t* mismatches_out) {
+    if (!c || !x || !mismatches_out || n < 1) GMC_FAIL(GMC_EINVAL, "gmc_debug_div_check: bad argument");
+    GMC_CUDA(cudaSetDevice(c->device));
+    unsigned long long* dm = nullptr;
+    GMC_CUDA(cudaMalloc(&dm, sizeof(unsigned long long)));
+    GMC_CUDA(cudaMemset(dm, 0, sizeof(unsigned long long)));
+    div_check_kernel<<<(unsigned)((n + 255) / 256), 256>>>(x, n, divisor, 1.0 / divisor, dm);
+    unsigned long long h = 0;
+    GMC_CUDA(cudaMemcpy(&h, dm, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(dm);
+    *mismatches_out = (int64_t)h;
     return GMC_OK;
 }

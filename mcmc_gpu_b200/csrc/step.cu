@@ -27,6 +27,21 @@ struct FastDiv {
     __device__ __forceinline__ int div(int t) const { return d == 1 ? t : (int)__umulhi((uint32_t)t, m); }
 };
 
+// Optional per-phase cycle accounting (thread 0 of each CTA; enabled when the host passes a buffer): used by
+// profiles/phase_timing.py to attribute the step time without relying on SASS line tables.
+struct PhaseClock {
+    long long* acc;      // [GMC_N_PHASES] global, atomically accumulated; nullptr = disabled
+    long long t;
+    __device__ __forceinline__ void start() { if (acc && threadIdx.x == 0) t = clock64(); }
+    __device__ __forceinline__ void mark(int phase) {
+        if (acc && threadIdx.x == 0) {
+            const long long n = clock64();
+            atomicAdd(reinterpret_cast<unsigned long long*>(acc + phase), (unsigned long long)(n - t));
+            t = n;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------------------------
 // complex helpers
 // ---------------------------------------------------------------------------------------------------------------
@@ -288,7 +303,7 @@ template <bool INJECT>
 __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, int pair_idx, double scale, double nug,
                                  double range_x, double range_y, const Philox& rng, uint32_t it_lo, uint32_t it_hi,
                                  const double* __restrict__ z_re, const double* __restrict__ z_im,
-                                 const double* __restrict__ z_nug, bool apply_taper) {
+                                 const double* __restrict__ z_nug, bool apply_taper, PhaseClock& pc) {
     __shared__ GmcFftPlan s_plan[2];
     const GmcPair pr = d.pairs[pair_idx];
     const int h = pr.h, w = pr.w, n2 = w / 2, hc = n2 + 1, pitchc = pr.pitchc;
@@ -352,9 +367,11 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
     const double inv_n = 1.0 / ((double)h * (double)w);
     const double sd = sqrt(power) * inv_n;
     const double cscale = scale / (sd + 1e-12) * inv_n;
+    pc.mark(1);
 
     // (2) inverse DFT along y for the w/2+1 stored columns
     fft_lines<false>(Z, pitchc, ph, hc, d.twiddle);
+    pc.mark(2);
 
     // (3) real-row recombination: Y_k = (X_k + conj X_{n2-k}) + i (X_k - conj X_{n2-k}) e^{+2 pi i k/w}, k < n2, stored
     // at the digit-reversed position of the row pass.  One warp per row; a lane owns the pair (k, n2-k), reads both, and
@@ -394,9 +411,11 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
         }
         __syncthreads();
     }
+    pc.mark(3);
 
     // (4) inverse DFT of length w/2 along x: row y now holds (f[y][2m], f[y][2m+1]) as its m-th complex entry
     fft_lines<true>(Z, pitchc, pw, h, d.twiddle);
+    pc.mark(4);
 
     FieldView fv;
     fv.F = buf;
@@ -446,7 +465,8 @@ __device__ __forceinline__ void prefetch_block(const StepScalars& s, int H, int 
 template <bool INJECT_F>
 __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, const FieldView& fv, const double* f_inj,
                           int f_pitch, const Philox& rng, uint32_t it_lo, uint32_t it_hi, double* tile, double* newres,
-                          double* bed, double* mcres, double& ssq, int32_t* resampled, double* loss_next_out) {
+                          double* bed, double* mcres, double& ssq, int32_t* resampled, double* loss_next_out,
+                          PhaseClock& pc) {
     const int H = d.H, W = d.W;
     const StepScalars s = *sc;
     const int bh = s.x1 - s.x0, bw = s.y1 - s.y0;
@@ -489,6 +509,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
         }
     }
     __syncthreads();
+    pc.mark(5);
 
     // phase B: residual on the block, loss delta, thickness guard                       MCMC.py:1292-1329
     double delta = 0.0;
@@ -549,6 +570,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
         scratch[35] = loss_next;
     }
     __syncthreads();
+    pc.mark(6);
     const int accept = sc->accept;
     if (loss_next_out && threadIdx.x == 0) *loss_next_out = scratch[35];
     if (accept) {
@@ -562,6 +584,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
         }
     }
     __syncthreads();   // write-back visible to the next iteration's tile load; smem free for reuse
+    pc.mark(7);
 }
 
 // full masked nansum of the tracked residual (fixed order)
@@ -580,10 +603,11 @@ __device__ double resync_ssq(const GmcDev& d, const double* mcres, double* scrat
 // ---------------------------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char gmc_smem[];
 
-__global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
+__global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
     run_kernel(GmcDev d, double* bed_all, double* mcres_all, double* ssq_all, const uint64_t* __restrict__ seeds,
                uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache,
-               int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int resync_every, int tile_off) {
+               int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int resync_every, int tile_off,
+               long long* phase_acc) {
     __shared__ double scratch[40];
     __shared__ StepScalars sc;
     double* buf = reinterpret_cast<double*>(gmc_smem);
@@ -594,6 +618,9 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
     int32_t* resampled = resampled_all ? resampled_all + c * plane : nullptr;
     const Philox rng(seeds[c]);
     double ssq = ssq_all[c];
+    PhaseClock pc;
+    pc.acc = phase_acc;
+    pc.start();
 
     for (int k = 0; k < n_steps; ++k) {
         const uint64_t it = iter0 + (uint64_t)k;
@@ -631,11 +658,12 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
         }
         __syncthreads();
         prefetch_block(sc, d.H, d.W, bed, mcres);
+        pc.mark(0);
         const FieldView fv = synth_field<false>(d, buf, scratch, sc.pair, sc.scale, sc.nug, sc.range_x, sc.range_y, rng, it_lo,
-                                                it_hi, nullptr, nullptr, nullptr, true);
+                                                it_hi, nullptr, nullptr, nullptr, true, pc);
         // tile after the field; the new residuals reuse the field's storage once the tile is built (f is dead by then)
         step_tail<false>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
-                         nullptr);
+                         nullptr, pc);
         if (threadIdx.x == 0) {
             const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
             if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
@@ -670,9 +698,11 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS)
     double ssq = ssq_all[c];
     const Philox rng(0ull);
     FieldView fv = {};
+    PhaseClock pc;
+    pc.acc = nullptr;
     step_tail<true>(d, &sc, scratch, fv, f_all + c * f_stride, sc.w, rng, 0u, 0u, buf + (int64_t)hmax * wmax, buf,
                     bed_all + c * plane, mcres_all + c * plane, ssq, resampled_all ? resampled_all + c * plane : nullptr,
-                    loss_next_out ? loss_next_out + c : nullptr);
+                    loss_next_out ? loss_next_out + c : nullptr, pc);
     if (threadIdx.x == 0) {
         ssq_all[c] = ssq;
         if (accepted_out) accepted_out[c] = (uint8_t)sc.accept;
@@ -681,7 +711,7 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS)
 }
 
 template <bool INJECT>
-__global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
+__global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
     field_kernel(GmcDev d, const int32_t* __restrict__ pair, const double* __restrict__ scale, const double* __restrict__ nug,
                  const double* __restrict__ range_x, const double* __restrict__ range_y, const double* __restrict__ z_re,
                  const double* __restrict__ z_im, const double* __restrict__ z_nug, const uint64_t* __restrict__ seeds,
@@ -692,9 +722,11 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, 2)
     const int p = pair[i];
     const Philox rng(INJECT ? 0ull : seeds[i]);
     const uint32_t it_lo = (uint32_t)iter, it_hi = (uint32_t)(iter >> 32);
+    PhaseClock pc;
+    pc.acc = nullptr;
     const FieldView fv = synth_field<INJECT>(d, buf, scratch, p, scale[i], nug[i], range_x[i], range_y[i], rng, it_lo, it_hi,
                                              INJECT ? z_re + i * stride : nullptr, INJECT ? z_im + i * stride : nullptr,
-                                             INJECT ? z_nug + i * stride : nullptr, apply_taper != 0);
+                                             INJECT ? z_nug + i * stride : nullptr, apply_taper != 0, pc);
     const int h = d.pairs[p].h, w = d.pairs[p].w;
     const FastDiv dw(w);
     for (int e = threadIdx.x; e < h * w; e += GMC_STEP_THREADS) {
@@ -805,8 +837,25 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
     run_kernel<<<C, GMC_STEP_THREADS, c->step_smem_bytes, (cudaStream_t)stream>>>(c->dev, bed, mcres, ssq, seeds, iter0, n_steps,
                                                                                  loss_cache, step_cache, blocks_cache,
                                                                                  cache_stride, cache_offset, resampled,
-                                                                                 resync_every, c->step_tile_off);
+                                                                                 resync_every, c->step_tile_off, c->d_phase);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+// ---- debug: per-phase cycle accounting of run_kernel ---------------------------------------------------------
+extern "C" int gmc_debug_phase_timing(gmc_ctx* c, int enable, int64_t* cycles_out) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_debug_phase_timing: ctx is NULL");
+    GMC_CUDA(cudaSetDevice(c->device));
+    if (cycles_out && c->d_phase) {
+        GMC_CUDA(cudaDeviceSynchronize());
+        GMC_CUDA(cudaMemcpy(cycles_out, c->d_phase, GMC_N_PHASES * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !c->d_phase) GMC_CUDA(cudaMalloc(&c->d_phase, GMC_N_PHASES * sizeof(long long)));
+    if (enable) GMC_CUDA(cudaMemset(c->d_phase, 0, GMC_N_PHASES * sizeof(long long)));
+    if (!enable && c->d_phase) {
+        cudaFree(c->d_phase);
+        c->d_phase = nullptr;
+    }
     return GMC_OK;
 }

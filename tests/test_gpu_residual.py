@@ -102,3 +102,23 @@ def test_errors_are_loud():
         ctx.residual(big, torch.empty_like(big))
     with pytest.raises(GmcShapeError):
         Context(1, 8, 1)
+
+
+@pytest.mark.parametrize("divisor", [500.0, 1000.0, 125.0, 250.0, 0.1, 3.0, 7e-3, 1.0 / 3.0, 999.9999999999999, 1.9999999999999998, 1.0000000000000002])
+def test_division_by_constant_is_correctly_rounded(divisor):
+    """The stencil divides by res and 2*res through a reciprocal + one FMA residual correction; it must return the same
+    bits as IEEE division (numpy's `/`) for every dividend: random, near powers of two, huge, tiny, zero, inf, nan."""
+    import torch
+    from mcmc_gpu_b200._lib import Context
+    ctx = Context(4, 4, 1)
+    g = np.random.default_rng(int(divisor * 1000) % 2 ** 31)
+    n = 1 << 22
+    x = np.concatenate([
+        g.standard_normal(n) * 10.0 ** g.integers(-12, 12, n),
+        np.ldexp(1.0 + g.integers(0, 4, n // 4) * 2.0 ** -52, g.integers(-60, 60, n // 4)) * divisor,     # quotients next to 2^k
+        np.ldexp(2.0 - g.integers(1, 4, n // 4) * 2.0 ** -52, g.integers(-60, 60, n // 4)) * divisor,
+        (g.integers(1, 2 ** 53, n // 4).astype(np.float64)) * divisor,                                       # exact-ish quotients
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-320, -1e-320, 1e308, -1e308, 5e-324, 1e-300, 1e300, 2.0 ** -1022]),
+    ])
+    xd = torch.as_tensor(x).cuda()
+    assert ctx.div_check(xd, divisor) == 0
