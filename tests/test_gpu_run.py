@@ -119,3 +119,31 @@ def test_two_sample_agreement_with_reference_rng():
     p_acc = ks_2samp(acc_o, acc_g).pvalue
     p_loss = ks_2samp(loss_o, loss_g).pvalue
     assert p_acc > 1e-3 and p_loss > 1e-3, (p_acc, p_loss)
+
+
+def test_driver_checkpoint_resume_and_ensemble(tmp_path):
+    """largeScaleChain_mp on the GPU: reference file layout, resume continues the Philox counters (two runs of 11
+    iterations == one uninterrupted chain of 20 proposals for the zero-rim taper), ensemble moments == numpy."""
+    import torch
+    from mcmc_gpu_b200 import MCMC, drivers
+    case = dict(TRAJECTORY_CASES["tutorial200"])
+    ch, rf, g = product_chain(case)
+    seeds = [31, 32, 33]
+    beds0 = [g["bed0"] + 0.25 * k for k in range(3)]
+    r1 = quiet(drivers.largeScaleChain_mp, 3, 8, ch, rf, beds0, seeds, [11] * 3, str(tmp_path))
+    r2 = quiet(drivers.largeScaleChain_mp, 3, 8, ch, rf, beds0, seeds, [11] * 3, str(tmp_path))
+    batch = MCMC.ChainBatch(ch, rf, np.stack(beds0), [MCMC.philox_key(s, s) for s in seeds], track_resampled=True)
+    batch.advance(10)
+    lc, st, bl = batch.advance(10)
+    for k in range(3):
+        assert bits_equal(batch.beds()[k], r2[k][0])
+        assert np.array_equal(st[k], r2[k][4][1:].astype(np.uint8))
+        folder = tmp_path / "LargeScaleChain" / str(seeds[k])
+        assert int(np.loadtxt(folder / "current_iter.txt")) == 22
+        assert bits_equal(np.load(folder / "bed_0k.npy"), r2[k][0])
+        with np.load(folder / "results_0k.npz") as z:
+            assert z["loss"].shape == (22,) and np.array_equal(z["resampled_times"], r1[k][5] + r2[k][5])
+    mean, var = drivers.ensemble_mean_var(batch, g["bed0"])
+    stack = batch.beds()
+    assert np.allclose(mean.cpu().numpy(), stack.mean(0), rtol=0, atol=1e-9)
+    assert np.allclose(var.cpu().numpy(), stack.var(0), rtol=1e-9, atol=1e-12)
