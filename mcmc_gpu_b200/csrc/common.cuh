@@ -57,11 +57,13 @@ struct GmcFftPlan {
 // per block-size pair
 struct GmcPair {
     int h, w;            // field shape [h][w] (rows, cols)
-    int plan_h, plan_w2; // indices into ctx->plans: column transform of length h, row transform of length w/2
     int pitchc;          // row pitch of the half plane in double2 units (>= w/2+1, odd)
     int ksq_off_h, ksq_off_w;  // offsets (in double) of (2 pi fftfreq(n, d))^2, k in [0, n/2], for n = h and n = w
     int64_t mask_off;    // offset (in double) of the taper in ctx->d_edge_masks
+    GmcFftPlan ph, pw;   // column transform of length h, row transform of length w/2 (copied in: one load gets all)
 };
+
+#define GMC_MAX_EDGE 128   // largest block edge (bounded anyway by one SM's shared memory)
 
 struct GmcFieldModel {
     int model;
@@ -82,16 +84,19 @@ struct GmcDev {
     const double* dhdt;
     const double* smb;
     const double* crf_weight;   // NULL for block_type 'RF'
+    const double2* sv;          // packed {surf, velx} per cell: one 16 B load feeds an x-flux
+    const double2* sy;          // packed {surf, vely} per cell: one 16 B load feeds a y-flux
+    const double2* ds;          // packed {dhdt, smb} per cell
     const uint8_t* flags;       // bit0 gate, bit1 mc
     const int32_t* centre_cells;
     int64_t n_centre_cells;
     double res;                 // chain.resolution
     double two_res;             // 2.*res
     double two_sigma2;          // 2*sigma_mc**2
+    double r_res, r_two_res;    // RN(1/res), RN(1/(2 res)) for div_const
     // block table
     int n_pairs;
     const GmcPair* pairs;
-    const GmcFftPlan* plans;
     const double2* twiddle;
     const int16_t* perm;
     const int16_t* pos;
@@ -113,7 +118,6 @@ struct gmc_ctx {
     double* d_partials;    // [max_chains][n_tiles] loss partials
     int n_tiles;
     GmcPair* d_pairs;
-    GmcFftPlan* d_plans;
     double2* d_twiddle;
     int16_t* d_perm;
     int16_t* d_pos;
@@ -142,6 +146,19 @@ __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// x / d for a loop-invariant d with r = RN(1/d): q = RN(x r), rem = x - d q (exact in one FMA), q' = RN(q + rem r).
+// This is the final correction step of the IEEE division routine; with a correctly rounded reciprocal it returns
+// RN(x/d) whenever no intermediate over/underflows, which the exponent guard ensures (else the true division runs).
+// tests/test_gpu_residual.py checks it against __ddiv_rn on random and adversarial operands.
+static __device__ __noinline__ double div_slow(double x, double d) { return __ddiv_rn(x, d); }
+__device__ __forceinline__ double div_const(double x, double d, double r) {
+    const double q = __dmul_rn(x, r);
+    const int e = __double2hiint(q) & 0x7fffffff;
+    if (e >= 0x05d00000 && e <= 0x7a100000) return fma(fma(-d, q, x), r, q);   // |q| in [2^-930, 2^930]
+    if (x == 0.0) return q;                     // +-0 / d: q already carries the right sign
+    return div_slow(x, d);                      // subnormal, huge, inf, nan: rare, kept out of line
+}
 
 // ---- Philox4x32-10 (Salmon et al. 2011), counter-based: any draw is addressable by (key, counter) -------------
 struct Philox {
@@ -182,7 +199,7 @@ __device__ __forceinline__ uint64_t bounded_u64(uint32_t hi, uint32_t lo, uint64
     return __umul64hi(((uint64_t)hi << 32) | lo, n);
 }
 // two independent N(0,1) from one Philox block
-__device__ __forceinline__ void box_muller(const uint4 r, double& z0, double& z1) {
+static __device__ __noinline__ void box_muller(const uint4 r, double& z0, double& z1) {
     const double u1 = u01_open(r.x, r.y);
     const double u2 = u01_open(r.z, r.w);
     const double rad = sqrt(-2.0 * log(u1));

@@ -52,7 +52,6 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->d_centre = nullptr;
     c->d_partials = nullptr;
     c->d_pairs = nullptr;
-    c->d_plans = nullptr;
     c->d_twiddle = nullptr;
     c->d_perm = c->d_pos = nullptr;
     c->d_ksq = nullptr;
@@ -79,7 +78,6 @@ extern "C" int gmc_destroy(gmc_ctx* c) {
     cudaFree(c->d_centre);
     cudaFree(c->d_partials);
     cudaFree(c->d_pairs);
-    cudaFree(c->d_plans);
     cudaFree(c->d_twiddle);
     cudaFree(c->d_perm);
     cudaFree(c->d_pos);
@@ -102,11 +100,24 @@ extern "C" int gmc_set_static(gmc_ctx* c, const double* surf, const double* velx
         GMC_FAIL(GMC_EINVAL, "gmc_set_static: centre_cells/n_centre_cells inconsistent");
     GMC_CUDA(cudaSetDevice(c->device));
     const size_t n = (size_t)c->H * c->W;
-    if (!c->d_static) GMC_CUDA(cudaMalloc(&c->d_static, 6 * n * sizeof(double)));
+    if (!c->d_static) GMC_CUDA(cudaMalloc(&c->d_static, 12 * n * sizeof(double)));   // 6 planes + 3 packed pair arrays
     if (!c->d_flags) GMC_CUDA(cudaMalloc(&c->d_flags, n));
     const double* src[6] = {surf, velx, vely, dhdt, smb, crf_weight};
     for (int k = 0; k < 6; ++k)
         if (src[k]) GMC_CUDA(cudaMemcpy(c->d_static + k * n, src[k], n * sizeof(double), cudaMemcpyDefault));
+    {   // packed pairs for the step kernel's block stencil (one 16 B load per flux operand)
+        std::vector<double> h(5 * n), pk(6 * n);
+        GMC_CUDA(cudaMemcpy(h.data(), c->d_static, 5 * n * sizeof(double), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) {
+            pk[2 * i] = h[i];                    // sv = {surf, velx}
+            pk[2 * i + 1] = h[n + i];
+            pk[2 * n + 2 * i] = h[i];            // sy = {surf, vely}
+            pk[2 * n + 2 * i + 1] = h[2 * n + i];
+            pk[4 * n + 2 * i] = h[3 * n + i];    // ds = {dhdt, smb}
+            pk[4 * n + 2 * i + 1] = h[4 * n + i];
+        }
+        GMC_CUDA(cudaMemcpy(c->d_static + 6 * n, pk.data(), 6 * n * sizeof(double), cudaMemcpyHostToDevice));
+    }
     // pack the two masks into one flag byte per cell (host side; setup is not on the hot path)
     std::vector<uint8_t> g(n), m(n), fl(n);
     GMC_CUDA(cudaMemcpy(g.data(), gate_mask, n, cudaMemcpyDefault));
@@ -133,6 +144,11 @@ extern "C" int gmc_set_static(gmc_ctx* c, const double* surf, const double* velx
     d.dhdt = c->d_static + 3 * n;
     d.smb = c->d_static + 4 * n;
     d.crf_weight = crf_weight ? c->d_static + 5 * n : nullptr;
+    d.sv = reinterpret_cast<const double2*>(c->d_static + 6 * n);
+    d.sy = reinterpret_cast<const double2*>(c->d_static + 8 * n);
+    d.ds = reinterpret_cast<const double2*>(c->d_static + 10 * n);
+    d.r_res = 1.0 / resolution;
+    d.r_two_res = 1.0 / (2.0 * resolution);
     d.flags = c->d_flags;
     d.centre_cells = c->d_centre;
     d.n_centre_cells = n_centre_cells;
@@ -266,13 +282,15 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
         if (h > c->H || w > c->W)
             GMC_FAIL(GMC_ESHAPE, "gmc_set_blocks: pair %d (%dx%d) is larger than the %dx%d grid", i, h, w, c->H, c->W);
         if (w > 32767 || h > 32767) GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: block edge > 32767");
-        if (w / 2 / 2 + 1 > 64) GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: block width %d > 252 is not supported", w);
         pairs[i].h = h;
         pairs[i].w = w;
-        pairs[i].plan_h = plan_for(h);
-        pairs[i].plan_w2 = plan_for(w / 2);
-        if (pairs[i].plan_h < 0 || pairs[i].plan_w2 < 0)
+        if (h > GMC_MAX_EDGE || w > GMC_MAX_EDGE)
+            GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: pair %d (%dx%d) exceeds the largest supported block edge %d", i, h, w, GMC_MAX_EDGE);
+        const int ip = plan_for(h), iw = plan_for(w / 2);
+        if (ip < 0 || iw < 0)
             GMC_FAIL(GMC_EUNSUPPORTED, "gmc_set_blocks: pair %d (%dx%d) has a prime factor >= %d", i, h, w, GMC_MAX_RADIX);
+        pairs[i].ph = plans[ip];
+        pairs[i].pw = plans[iw];
         pairs[i].pitchc = (w / 2 + 1) | 1;                 // odd pitch (in 16 B units): bank-conflict-free row pass
         pairs[i].ksq_off_h = ksq_for(h);
         pairs[i].ksq_off_w = ksq_for(w);
@@ -282,14 +300,12 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
         mw = std::max(mw, w);
     }
     cudaFree(c->d_pairs);
-    cudaFree(c->d_plans);
     cudaFree(c->d_twiddle);
     cudaFree(c->d_perm);
     cudaFree(c->d_pos);
     cudaFree(c->d_ksq);
     cudaFree(c->d_edge_masks);
     c->d_pairs = nullptr;
-    c->d_plans = nullptr;
     c->d_twiddle = nullptr;
     c->d_perm = c->d_pos = nullptr;
     c->d_ksq = nullptr;
@@ -299,7 +315,6 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
     GMC_CUDA(cudaMalloc(&(dst), (vec).size() * sizeof((vec)[0])));                                 \
     GMC_CUDA(cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
     UPLOAD(c->d_pairs, pairs);
-    UPLOAD(c->d_plans, plans);
     UPLOAD(c->d_twiddle, tw);
     UPLOAD(c->d_perm, perm);
     UPLOAD(c->d_pos, pos);
@@ -314,7 +329,6 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
     GmcDev& d = c->dev;
     d.n_pairs = n_pairs;
     d.pairs = c->d_pairs;
-    d.plans = c->d_plans;
     d.twiddle = c->d_twiddle;
     d.perm = c->d_perm;
     d.pos = c->d_pos;

@@ -35,18 +35,6 @@
 #define RS_MIN_CTAS 4                 // 4 CTAs/SM: 46.7 KB of staged statics each, <= 128 registers per thread
 #endif
 
-// x / d for a loop-invariant d with r = RN(1/d): q = RN(x r), rem = x - d q (exact in one FMA), q' = RN(q + rem r).
-// This is the final correction step of the IEEE division routine; with a correctly rounded reciprocal it returns
-// RN(x/d) whenever no intermediate over/underflows, which the magnitude guard ensures (else the true division runs).
-// tests/test_gpu_residual.py checks it against __ddiv_rn on random and adversarial operands.
-__device__ __noinline__ double div_slow(double x, double d) { return div_rn(x, d); }
-__device__ __forceinline__ double div_const(double x, double d, double r) {
-    const double q = mul_rn(x, r);
-    const double aq = fabs(q);
-    if (aq > 1e-280 && aq < 1e280) return fma(fma(-d, q, x), r, q);
-    return div_slow(x, d);       // zero, subnormal, huge, inf, nan: rare, kept out of line
-}
-
 struct ResSmem {
     double surf[RS_TH + 2][RS_PITCH];
     double velx[RS_TH][RS_PITCH];
@@ -382,7 +370,7 @@ static int check_common(gmc_ctx* c, const void* p, int C, const char* who) {
 
 template <bool WR, bool LS>
 static void launch_variant(gmc_ctx* c, dim3 grid, cudaStream_t st, const double* bed, double* res, int C, bool vec) {
-    const double r_res = 1.0 / c->dev.res, r_two = 1.0 / c->dev.two_res;
+    const double r_res = c->dev.r_res, r_two = c->dev.r_two_res;
     const size_t smem = sizeof(ResSmem);
     if (vec) {
         cudaFuncSetAttribute(residual_kernel<WR, LS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

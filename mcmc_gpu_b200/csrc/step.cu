@@ -13,11 +13,20 @@
 //       the kernel (MCMC.py:1263-1360).  HBM sees the bed halo tile, the old block residual and, on accept, the write-back.
 #include "common.cuh"
 
+struct SpecParams {
+    int model;
+    double a;        // sqrt(len_x*len_y)
+    double nu;
+    double constant; // Matern prefactor
+    double kappa;    // 2 nu / a^2
+};
+
 struct StepScalars {
     int pair, h, w, ix, iy;
     int x0, x1, y0, y1, mx0, my0;
     double scale, nug, range_x, range_y, u;
     int accept;
+    SpecParams spec;
 };
 
 // exact t / d for t * d < 2^32 with one multiply-high
@@ -89,7 +98,7 @@ __device__ __forceinline__ void dft_odd(double2* v, const double2* __restrict__ 
     constexpr int HALF = (R - 1) / 2;
     double2 w[HALF + 1];
 #pragma unroll
-    for (int m = 1; m <= HALF; ++m) w[m] = __ldg(tw + m * step_r);
+    for (int m = 1; m <= HALF; ++m) w[m] = tw[m * step_r];
     double2 a[HALF + 1], b[HALF + 1];
     double2 sum0 = v[0];
 #pragma unroll
@@ -118,22 +127,23 @@ __device__ __forceinline__ void dft_odd(double2* v, const double2* __restrict__ 
     }
 }
 
-// One radix-R decimation-in-time stage over `count` independent lines of length n, in place.
-// ALONG_ROW: the transform runs along x (contiguous) and lanes map to different rows (pitch is odd in double2 units =>
-// conflict-free); otherwise it runs along y and lanes map to adjacent columns.
-template <int R, bool ALONG_ROW>
-__device__ __forceinline__ void fft_stage(double2* Z, int pitch, int n, int count, int L, const double2* __restrict__ tw) {
+// One radix-R decimation-in-time stage over `count` independent lines of length n, in place.  Element p of line l is
+// Z[l * line_stride + p * elem_stride]: the column pass has (1, pitch) — lanes on adjacent columns — and the row pass
+// (pitch, 1) with lanes on different rows (the pitch is odd in double2 units, so both are bank-conflict free).
+template <int R>
+__device__ __forceinline__ void fft_stage(double2* Z, int line_stride, int elem_stride, int n, int count, int L,
+                                          const double2* __restrict__ tw) {
     const int M = L / R;
     const int step = n / L;
     const int items = (n / R) * count;
     const FastDiv dcount(count), dM(M);
+    const int stride = M * elem_stride;
     for (int t = threadIdx.x; t < items; t += GMC_STEP_THREADS) {
         const int bf = dcount.div(t);
         const int line = t - bf * count;
         const int blk = dM.div(bf), k1 = bf - blk * M;
         const int base = blk * L + k1;
-        double2* p0 = ALONG_ROW ? Z + line * pitch + base : Z + base * pitch + line;
-        const int stride = ALONG_ROW ? M : M * pitch;
+        double2* p0 = Z + line * line_stride + base * elem_stride;
         double2 v[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) v[q] = p0[q * stride];
@@ -142,7 +152,7 @@ __device__ __forceinline__ void fft_stage(double2* Z, int pitch, int n, int coun
             int iq = i1;
 #pragma unroll
             for (int q = 1; q < R; ++q) {
-                v[q] = cmul(v[q], __ldg(tw + iq));
+                v[q] = cmul(v[q], tw[iq]);
                 iq += i1;
                 if (iq >= n) iq -= n;
             }
@@ -158,8 +168,7 @@ __device__ __forceinline__ void fft_stage(double2* Z, int pitch, int n, int coun
 
 // Fallback for any other prime radix R < GMC_MAX_RADIX (block edges such as 58 = 2*29): O(R^2) per butterfly with the
 // inputs parked in local memory.  Slow but rare; the default block sizes never take it.
-template <bool ALONG_ROW>
-__device__ __noinline__ void fft_stage_generic(double2* Z, int pitch, int n, int count, int L, int R,
+__device__ __noinline__ void fft_stage_generic(double2* Z, int line_stride, int elem_stride, int n, int count, int L, int R,
                                                const double2* __restrict__ tw) {
     const int M = L / R;
     const int step = n / L;
@@ -170,13 +179,12 @@ __device__ __noinline__ void fft_stage_generic(double2* Z, int pitch, int n, int
         const int line = t % count;
         const int bf = t / count;
         const int blk = bf / M, k1 = bf - blk * M;
-        const int base = blk * L + k1;
+        double2* p0 = Z + line * line_stride + (blk * L + k1) * elem_stride;
         const int i1 = k1 * step;
         int iq = 0;
         for (int q = 0; q < R; ++q) {
-            const int p = base + q * M;
-            const double2 x = ALONG_ROW ? Z[line * pitch + p] : Z[p * pitch + line];
-            v[q] = (q == 0 || L == R) ? x : cmul(x, __ldg(tw + iq));
+            const double2 x = p0[q * M * elem_stride];
+            v[q] = (q == 0 || L == R) ? x : cmul(x, tw[iq]);
             iq += i1;
             if (iq >= n) iq -= n;
         }
@@ -186,32 +194,29 @@ __device__ __noinline__ void fft_stage_generic(double2* Z, int pitch, int n, int
             for (int q = 1; q < R; ++q) {
                 m += k;
                 if (m >= R) m -= R;
-                acc = cadd(acc, cmul(v[q], __ldg(tw + m * step_r)));
+                acc = cadd(acc, cmul(v[q], tw[m * step_r]));
             }
-            const int p = base + k * M;
-            if (ALONG_ROW) Z[line * pitch + p] = acc;
-            else Z[p * pitch + line] = acc;
+            p0[k * M * elem_stride] = acc;
         }
     }
 }
 
-template <bool ALONG_ROW>
-__device__ void fft_lines(double2* Z, int pitch, const GmcFftPlan& plan, int count, const double2* __restrict__ tw_all) {
-    const double2* tw = tw_all + plan.tw_off;
+// All stages of one pass.  Kept out of line: the column and the row pass share one copy of the stage code (the step
+// kernel is instruction-cache sensitive).
+__device__ __noinline__ void fft_lines(double2* Z, int line_stride, int elem_stride, const GmcFftPlan& plan, int count,
+                                       const double2* __restrict__ tw) {
     int L = 1;
     for (int s = 0; s < plan.n_factors; ++s) {
         const int r = plan.radix[s];
         L *= r;
         switch (r) {
-            case 2: fft_stage<2, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            case 3: fft_stage<3, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            case 4: fft_stage<4, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            case 5: fft_stage<5, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            case 7: fft_stage<7, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            case 8: fft_stage<8, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            case 11: fft_stage<11, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            case 13: fft_stage<13, ALONG_ROW>(Z, pitch, plan.n, count, L, tw); break;
-            default: fft_stage_generic<ALONG_ROW>(Z, pitch, plan.n, count, L, r, tw); break;
+            case 2: fft_stage<2>(Z, line_stride, elem_stride, plan.n, count, L, tw); break;
+            case 3: fft_stage<3>(Z, line_stride, elem_stride, plan.n, count, L, tw); break;
+            case 4: fft_stage<4>(Z, line_stride, elem_stride, plan.n, count, L, tw); break;
+            case 5: fft_stage<5>(Z, line_stride, elem_stride, plan.n, count, L, tw); break;
+            case 7: fft_stage<7>(Z, line_stride, elem_stride, plan.n, count, L, tw); break;
+            case 8: fft_stage<8>(Z, line_stride, elem_stride, plan.n, count, L, tw); break;
+            default: fft_stage_generic(Z, line_stride, elem_stride, plan.n, count, L, r, tw); break;
         }
         __syncthreads();
     }
@@ -220,13 +225,8 @@ __device__ void fft_lines(double2* Z, int pitch, const GmcFftPlan& plan, int cou
 // ---------------------------------------------------------------------------------------------------------------
 // spectral amplitude sqrt(S(k))                                                          MCMC.py:209-239
 // ---------------------------------------------------------------------------------------------------------------
-struct SpecParams {
-    int model;
-    double a;        // sqrt(len_x*len_y)
-    double nu;
-    double constant; // Matern prefactor
-    double kappa;    // 2 nu / a^2
-};
+// x^p for x > 0 as exp(p log x): relative error ~ |p log x| 2^-53 (<= 1e-14 here), about half the cost of pow()
+__device__ __forceinline__ double pow_pos(double x, double p) { return exp(p * log(x)); }
 
 __device__ __forceinline__ SpecParams make_spec(const GmcFieldModel& fm, double range_x, double range_y) {
     SpecParams sp;
@@ -248,13 +248,13 @@ __device__ __forceinline__ SpecParams make_spec(const GmcFieldModel& fm, double 
     sp.constant = 1.0;
     sp.kappa = 0.0;
     if (fm.model == GMC_MATERN) {
-        sp.constant = div_rn(fm.matern_num, mul_rn(fm.matern_gamma, pow(sp.a, mul_rn(2.0, sp.nu))));
+        sp.constant = div_rn(fm.matern_num, mul_rn(fm.matern_gamma, pow_pos(sp.a, mul_rn(2.0, sp.nu))));
         sp.kappa = div_rn(mul_rn(2.0, sp.nu), mul_rn(sp.a, sp.a));
     }
     return sp;
 }
 
-__device__ __forceinline__ double spec_amp(const SpecParams& sp, double ksq_sum) {
+__device__ __noinline__ double spec_amp(const SpecParams& sp, double ksq_sum) {
     const double k = add_rn(sqrt(ksq_sum), 1e-10);
     double S;
     if (sp.model == GMC_GAUSSIAN) {
@@ -262,10 +262,10 @@ __device__ __forceinline__ double spec_amp(const SpecParams& sp, double ksq_sum)
         S = exp(mul_rn(-0.5, mul_rn(ak, ak)));
     } else if (sp.model == GMC_EXPONENTIAL) {
         const double ak = mul_rn(sp.a, k);
-        S = div_rn(1.0, pow(add_rn(1.0, mul_rn(ak, ak)), 1.5));
+        S = div_rn(1.0, pow_pos(add_rn(1.0, mul_rn(ak, ak)), 1.5));
     } else {
         const double four_pi = 4 * 3.141592653589793;
-        S = mul_rn(sp.constant, pow(add_rn(sp.kappa, mul_rn(four_pi, mul_rn(k, k))), sub_rn(-sp.nu, 1.0)));
+        S = mul_rn(sp.constant, pow_pos(add_rn(sp.kappa, mul_rn(four_pi, mul_rn(k, k))), sub_rn(-sp.nu, 1.0)));
     }
     return sqrt(S);
 }
@@ -295,27 +295,55 @@ __device__ __forceinline__ double field_value(const FieldView& fv, int y, int x,
         else box_muller(rng((uint32_t)e, it_lo, it_hi, GMC_STREAM_NUGGET), z0, z1);
         f = add_rn(f, mul_rn(fv.sq_nug, z0));
     }
-    if (fv.taper) f = mul_rn(f, __ldg(fv.taper + y * fv.w + x));                       // MCMC.py:778
     return f;
 }
 
+// Per-step copies of the current block size's small tables: every later access is a shared-memory read instead of an
+// L2 round trip on the critical path (the SM's L1 is almost entirely carved out as shared memory).
+struct StepTables {
+    double2 tw_h[GMC_MAX_EDGE];            // e^{+2 pi i k/h}
+    double2 tw_w[GMC_MAX_EDGE / 2];        // e^{+2 pi i k/(w/2)}
+    double2 htw[GMC_MAX_EDGE / 2];         // e^{+2 pi i k/w}
+    double ksq_y[GMC_MAX_EDGE / 2 + 1], ksq_x[GMC_MAX_EDGE / 2 + 1];
+    int16_t pos_y[GMC_MAX_EDGE], pos_w[GMC_MAX_EDGE / 2];
+};
+
+__device__ __forceinline__ void stage_tables(const GmcDev& d, const GmcPair& pr, StepTables& T) {
+    const int h = pr.h, n2 = pr.w / 2;
+    for (int t = threadIdx.x; t < h; t += GMC_STEP_THREADS) {
+        T.tw_h[t] = __ldg(d.twiddle + pr.ph.tw_off + t);
+        T.pos_y[t] = __ldg(d.pos + pr.ph.pos_off + t);
+        if (t <= h / 2) T.ksq_y[t] = __ldg(d.ksq + pr.ksq_off_h + t);
+        if (t < n2) {
+            T.tw_w[t] = __ldg(d.twiddle + pr.pw.tw_off + t);
+            T.htw[t] = __ldg(d.twiddle + pr.pw.htw_off + t);
+            T.pos_w[t] = __ldg(d.pos + pr.pw.pos_off + t);
+        }
+        if (t <= n2) T.ksq_x[t] = __ldg(d.ksq + pr.ksq_off_w + t);
+    }
+    for (int t = h + threadIdx.x; t <= n2; t += GMC_STEP_THREADS) {       // w/2 >= h (wide blocks)
+        if (t < n2) {
+            T.tw_w[t] = __ldg(d.twiddle + pr.pw.tw_off + t);
+            T.htw[t] = __ldg(d.twiddle + pr.pw.htw_off + t);
+            T.pos_w[t] = __ldg(d.pos + pr.pw.pos_off + t);
+        }
+        T.ksq_x[t] = __ldg(d.ksq + pr.ksq_off_w + t);
+    }
+}
+
+// pr and T live in shared memory; the caller has staged T (stage_tables + __syncthreads).
 template <bool INJECT>
-__device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, int pair_idx, double scale, double nug,
-                                 double range_x, double range_y, const Philox& rng, uint32_t it_lo, uint32_t it_hi,
+__device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, const GmcPair& pr, const StepTables& T,
+                                 double scale, double nug, const SpecParams& sp, const Philox& rng, uint32_t it_lo, uint32_t it_hi,
                                  const double* __restrict__ z_re, const double* __restrict__ z_im,
                                  const double* __restrict__ z_nug, bool apply_taper, PhaseClock& pc) {
-    __shared__ GmcFftPlan s_plan[2];
-    const GmcPair pr = d.pairs[pair_idx];
     const int h = pr.h, w = pr.w, n2 = w / 2, hc = n2 + 1, pitchc = pr.pitchc;
-    if (threadIdx.x < 2) s_plan[threadIdx.x] = d.plans[threadIdx.x == 0 ? pr.plan_h : pr.plan_w2];
-    __syncthreads();
-    const GmcFftPlan& ph = s_plan[0];
-    const GmcFftPlan& pw = s_plan[1];
+    const GmcFftPlan& ph = pr.ph;
+    const GmcFftPlan& pw = pr.pw;
     double2* Z = reinterpret_cast<double2*>(buf);
-    const SpecParams sp = make_spec(d.fm, range_x, range_y);
-    const int16_t* posY = d.pos + ph.pos_off;
-    const double* ksqY = d.ksq + pr.ksq_off_h;
-    const double* ksqX = d.ksq + pr.ksq_off_w;
+    const int16_t* posY = T.pos_y;
+    const double* ksqY = T.ksq_y;
+    const double* ksqX = T.ksq_x;
     const double inv_sqrt2 = 0.70710678118654752440;
 
     // (1) fill the Hermitian half plane (ky in [0,h), kx in [0,w/2]) at the digit-reversed row position of the column
@@ -326,7 +354,7 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
     for (int q = threadIdx.x; q < (h / 2 + 1) * hc; q += GMC_STEP_THREADS) {
         const int a = dhc.div(q), kx = q - a * hc;
         // MCMC.py:224: k = sqrt(kxv**2 + kyv**2) + 1e-10
-        const double amp = spec_amp(sp, add_rn(__ldg(ksqX + kx), __ldg(ksqY + a)));
+        const double amp = spec_amp(sp, add_rn(ksqX[kx], ksqY[a]));
         const bool self_y = (a == 0 || 2 * a == h);
         const bool edge_x = (kx == 0 || kx == n2);
         const int a2 = self_y ? a : h - a;
@@ -339,27 +367,23 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
             X0 = make_double2(0.5 * amp * (z_re[e0] + z_re[m0]), 0.5 * amp * (z_im[e0] - z_im[m0]));
             X1 = make_double2(0.5 * amp * (z_re[e1] + z_re[m1]), 0.5 * amp * (z_im[e1] - z_im[m1]));
         } else {
-            double z0, z1;
+            // straight-line: both draws and sqrt(S) are independent dependency chains the scheduler can interleave
+            // (the second draw is unused for self-conjugate rows / Hermitian columns: < 10 % of the items)
+            double z0, z1, y0, y1;
             box_muller(rng((uint32_t)(a * w + kx), it_lo, it_hi, GMC_STREAM_NOISE), z0, z1);
-            if (self_y && edge_x) {
-                X0 = make_double2(amp * z0, 0.0);                  // self-conjugate point: real, variance S
-                X1 = X0;
-            } else {
-                X0 = make_double2(amp * inv_sqrt2 * z0, amp * inv_sqrt2 * z1);
-                if (edge_x) X1 = cconj(X0);                        // columns kx = 0, w/2 are Hermitian in ky
-                else if (!self_y) {
-                    box_muller(rng((uint32_t)(a2 * w + kx), it_lo, it_hi, GMC_STREAM_NOISE), z0, z1);
-                    X1 = make_double2(amp * inv_sqrt2 * z0, amp * inv_sqrt2 * z1);
-                } else X1 = X0;
-            }
+            box_muller(rng((uint32_t)(a2 * w + kx), it_lo, it_hi, GMC_STREAM_NOISE), y0, y1);
+            const double am = amp * inv_sqrt2;
+            const bool real_pt = self_y && edge_x;                 // self-conjugate point: real, variance S
+            X0 = make_double2(real_pt ? amp * z0 : am * z0, real_pt ? 0.0 : am * z1);
+            X1 = edge_x ? cconj(X0) : make_double2(am * y0, am * y1);   // columns kx = 0, w/2 are Hermitian in ky
         }
         if (a == 0 && kx == 0) X0 = X1 = make_double2(0.0, 0.0);   // DC: removed by the mean subtraction (MCMC.py:248)
         const double wgt = edge_x ? 1.0 : 2.0;
         power += wgt * (X0.x * X0.x + X0.y * X0.y);
-        Z[__ldg(posY + a) * pitchc + kx] = X0;
+        Z[posY[a] * pitchc + kx] = X0;
         if (!self_y) {
             power += wgt * (X1.x * X1.x + X1.y * X1.y);
-            Z[__ldg(posY + a2) * pitchc + kx] = X1;
+            Z[posY[a2] * pitchc + kx] = X1;
         }
     }
     power = block_sum<GMC_STEP_THREADS>(power, scratch);           // also orders the fill before the column pass
@@ -370,7 +394,7 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
     pc.mark(1);
 
     // (2) inverse DFT along y for the w/2+1 stored columns
-    fft_lines<false>(Z, pitchc, ph, hc, d.twiddle);
+    fft_lines(Z, 1, pitchc, ph, hc, T.tw_h);
     pc.mark(2);
 
     // (3) real-row recombination: Y_k = (X_k + conj X_{n2-k}) + i (X_k - conj X_{n2-k}) e^{+2 pi i k/w}, k < n2, stored
@@ -378,8 +402,8 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
     // only then writes, so the in-place permutation is safe (npairs <= 64).
     {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        const int16_t* posW = d.pos + pw.pos_off;
-        const double2* htw = d.twiddle + pw.htw_off;
+        const int16_t* posW = T.pos_w;
+        const double2* htw = T.htw;
         const int npairs = n2 / 2 + 1;
         for (int y = wid; y < h; y += GMC_STEP_THREADS / 32) {
             double2* row = Z + y * pitchc;
@@ -393,7 +417,7 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
                     const int kp = n2 - k;                         // partner (k = 0 pairs with the Nyquist entry n2)
                     const double2 xk = row[k], xp = row[kp];
                     const double2 E = cadd(xk, cconj(xp));
-                    const double2 O = cmul(csub(xk, cconj(xp)), (k == 0) ? make_double2(1.0, 0.0) : __ldg(htw + k));
+                    const double2 O = cmul(csub(xk, cconj(xp)), (k == 0) ? make_double2(1.0, 0.0) : htw[k]);
                     ya[it] = make_double2((E.x - O.y) * cscale, (E.y + O.x) * cscale);          // E + iO
                     ka[it] = k;
                     if (k != 0 && kp != k) {
@@ -405,8 +429,8 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 2; ++it) {
-                if (ka[it] >= 0) row[__ldg(posW + ka[it])] = ya[it];
-                if (kb[it] >= 0) row[__ldg(posW + kb[it])] = yb[it];
+                if (ka[it] >= 0) row[posW[ka[it]]] = ya[it];
+                if (kb[it] >= 0) row[posW[kb[it]]] = yb[it];
             }
         }
         __syncthreads();
@@ -414,7 +438,7 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
     pc.mark(3);
 
     // (4) inverse DFT of length w/2 along x: row y now holds (f[y][2m], f[y][2m+1]) as its m-th complex entry
-    fft_lines<true>(Z, pitchc, pw, h, d.twiddle);
+    fft_lines(Z, pitchc, 1, pw, h, T.tw_w);
     pc.mark(4);
 
     FieldView fv;
@@ -445,20 +469,37 @@ __device__ __forceinline__ double sq_or_zero(double v) { return (v == v) ? mul_r
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Pull the lines the tail will read (bed halo tile, old block residual) from HBM into L2 while the field is synthesised.
-__device__ __forceinline__ void prefetch_block(const StepScalars& s, int H, int W, const double* bed, const double* mcres) {
-    const int r0 = max(s.x0 - 1, 0), r1 = min(s.x1 + 1, H);
-    const int c0 = max(s.y0 - 1, 0), c1 = min(s.y1 + 1, W);
-    const int lines = ((c1 - c0) * 8 + 127) / 128 + 1;     // 128 B lines per row segment (+1: unaligned start)
-    const int total = (r1 - r0) * lines;
-    for (int t = threadIdx.x; t < 2 * total; t += GMC_STEP_THREADS) {
-        const int which = t >= total;
-        const int u = which ? t - total : t;
-        const int r = u / lines, l = u - r * lines;
-        const double* base = (which ? mcres : bed) + (int64_t)(r0 + r) * W + c0;
-        const char* p = reinterpret_cast<const char*>(base) + l * 128;
-        if (p < reinterpret_cast<const char*>(base + (c1 - c0))) prefetch_l2(p);
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Start the tail's HBM traffic at the top of the step, while the field is synthesised: the bed of the block plus its
+// one-cell halo lands asynchronously (cp.async) in the tile region, which is idle until the candidate is built; the
+// lines of the old block residual are pulled into L2.  Cells outside the grid become NaN (never used by the edge rules).
+__device__ __forceinline__ void stage_block_async(const StepScalars& s, int H, int W, const double* bed, const double* mcres,
+                                                  double* tile) {
+    const int bh = s.x1 - s.x0, bw = s.y1 - s.y0, tp = bw + 2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int ti = wid; ti < bh + 2; ti += GMC_STEP_THREADS / 32) {          // one warp per tile row: coalesced
+        const int i = s.x0 - 1 + ti;
+        const bool row_in = i >= 0 && i < H;
+        const double* src = bed + (int64_t)i * W + (s.y0 - 1);
+        double* dst = tile + ti * tp;
+        for (int tj = lane; tj < tp; tj += 32) {
+            const int j = s.y0 - 1 + tj;
+            if (row_in && j >= 0 && j < W) cp_async8(dst + tj, src + tj);
+            else dst[tj] = qnan;
+        }
+        if (ti >= 1 && ti <= bh) {                                          // old residual of this block row -> L2
+            const char* base = reinterpret_cast<const char*>(mcres + (int64_t)i * W + s.y0);
+            for (int off = lane * 128; off < bw * 8 + 127; off += 32 * 128)
+                prefetch_l2(base + min(off, bw * 8 - 8));
+        }
     }
+    cp_async_commit();
 }
 
 // Field source for the tail: either the synthesised field in shared memory (FieldView) or an injected f in global memory.
@@ -471,40 +512,44 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
     const StepScalars s = *sc;
     const int bh = s.x1 - s.x0, bw = s.y1 - s.y0;
     const int tp = bw + 2;
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    const FastDiv dtp(tp), dbw(bw);
+    const FastDiv dbw(bw);
 
-    // phase A: candidate tile = block + one-cell halo                                  MCMC.py:1279-1290
+    // phase A: candidate = bed + perturbation on the gated block cells (the tile already holds the bed, staged
+    // asynchronously at the top of the step); loads are issued in batches so one L2 round trip serves U cells.
+    cp_async_wait_all();
+    __syncthreads();
     {
-        constexpr int U = 4;
-        const int n_tile = (bh + 2) * tp;
-        for (int t0 = threadIdx.x; t0 < n_tile; t0 += U * GMC_STEP_THREADS) {
-            double v[U];
+        constexpr int U = 8;
+        const int n_blk = bh * bw;
+        for (int e0 = threadIdx.x; e0 < n_blk; e0 += U * GMC_STEP_THREADS) {
             uint8_t fl[U];
-            int64_t idx[U];
-            int ti[U], tj[U];
+            double tp_[U], cw[U];
+            int tpos[U], fy[U], fx[U];
 #pragma unroll
-            for (int k = 0; k < U; ++k) {                     // issue all loads of the batch first
-                const int t = t0 + k * GMC_STEP_THREADS;
-                ti[k] = dtp.div(t);
-                tj[k] = t - ti[k] * tp;
-                const int i = s.x0 - 1 + ti[k], j = s.y0 - 1 + tj[k];
-                const bool in = t < n_tile && i >= 0 && i < H && j >= 0 && j < W;
-                idx[k] = in ? (int64_t)i * W + j : -1;
-                v[k] = in ? __ldcg(bed + idx[k]) : qnan;
-                fl[k] = in ? __ldg(d.flags + idx[k]) : 0;
+            for (int k = 0; k < U; ++k) {
+                const int e = e0 + k * GMC_STEP_THREADS;
+                const bool on = e < n_blk;
+                const int bi = on ? dbw.div(e) : 0, bj = on ? e - bi * bw : 0;
+                const int64_t idx = (int64_t)(s.x0 + bi) * W + (s.y0 + bj);
+                fy[k] = s.mx0 + bi;
+                fx[k] = s.my0 + bj;
+                tpos[k] = (bi + 1) * tp + (bj + 1);
+                fl[k] = on ? __ldg(d.flags + idx) : 0;
+                cw[k] = (on && d.crf_weight) ? __ldg(d.crf_weight + idx) : 1.0;
+                tp_[k] = (on && !INJECT_F && fv.taper) ? __ldg(fv.taper + fy[k] * fv.w + fx[k]) : 1.0;
             }
 #pragma unroll
             for (int k = 0; k < U; ++k) {
-                const int t = t0 + k * GMC_STEP_THREADS;
-                if (t >= n_tile) break;
-                if (idx[k] >= 0 && ti[k] >= 1 && ti[k] <= bh && tj[k] >= 1 && tj[k] <= bw && (fl[k] & FLAG_GATE)) {
-                    const int fy = s.mx0 + ti[k] - 1, fx = s.my0 + tj[k] - 1;
-                    double p = INJECT_F ? f_inj[fy * f_pitch + fx] : field_value<false>(fv, fy, fx, rng, it_lo, it_hi);
-                    if (d.crf_weight) p = mul_rn(p, __ldg(d.crf_weight + idx[k]));
-                    v[k] = add_rn(v[k], p);
+                if (fl[k] & FLAG_GATE) {
+                    double p;
+                    if (INJECT_F) p = f_inj[fy[k] * f_pitch + fx[k]];
+                    else {
+                        p = field_value<false>(fv, fy[k], fx[k], rng, it_lo, it_hi);
+                        if (fv.taper) p = mul_rn(p, tp_[k]);                           // MCMC.py:778
+                    }
+                    if (d.crf_weight) p = mul_rn(p, cw[k]);                            // MCMC.py:1279-1282
+                    tile[tpos[k]] = add_rn(tile[tpos[k]], p);                          // MCMC.py:1285-1290
                 }
-                tile[t] = v[k];
             }
         }
     }
@@ -517,32 +562,28 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
     for (int e = threadIdx.x; e < bh * bw; e += GMC_STEP_THREADS) {
         const int bi = dbw.div(e), bj = e - bi * bw;
         const int i = s.x0 + bi, j = s.y0 + bj;
-        const int64_t idx = (int64_t)i * W + j;
         const double* tc = tile + (bi + 1) * tp + (bj + 1);
-        int jl = j - 1, jr = j + 1;
-        double denx = d.two_res;
-        if (j == 0) { jl = 0; denx = d.res; }
-        else if (j == W - 1) { jr = W - 1; denx = d.res; }
-        int iu = i - 1, id = i + 1;
-        double deny = d.two_res;
-        if (i == 0) { iu = 0; deny = d.res; }
-        else if (i == H - 1) { id = H - 1; deny = d.res; }
+        // np.gradient: one-sided at the grid edge (neighbour index clamped, divisor res), central elsewhere
+        const int jl = max(j - 1, 0), jr = min(j + 1, W - 1);
+        const int iu = max(i - 1, 0), id = min(i + 1, H - 1);
+        const bool ex = (j == 0) || (j == W - 1), ey = (i == 0) || (i == H - 1);
+        const double denx = ex ? d.res : d.two_res, rdx = ex ? d.r_res : d.r_two_res;
+        const double deny = ey ? d.res : d.two_res, rdy = ey ? d.r_res : d.r_two_res;
         const int64_t r = (int64_t)i * W;
-        // all global loads first
-        const double vxr = __ldg(d.velx + r + jr), sxr = __ldg(d.surf + r + jr);
-        const double vxl = __ldg(d.velx + r + jl), sxl = __ldg(d.surf + r + jl);
-        const double vyd = __ldg(d.vely + (int64_t)id * W + j), syd = __ldg(d.surf + (int64_t)id * W + j);
-        const double vyu = __ldg(d.vely + (int64_t)iu * W + j), syu = __ldg(d.surf + (int64_t)iu * W + j);
-        const double dh = __ldg(d.dhdt + idx), sm = __ldg(d.smb + idx), sc0 = __ldg(d.surf + idx);
-        const uint8_t fl = __ldg(d.flags + idx);
-        const double rold = __ldcg(mcres + idx);
-        const double fr = mul_rn(vxr, sub_rn(sxr, tc[jr - j]));
-        const double fl_ = mul_rn(vxl, sub_rn(sxl, tc[jl - j]));
-        const double dx = div_rn(sub_rn(fr, fl_), denx);
-        const double fd = mul_rn(vyd, sub_rn(syd, tc[(id - i) * tp]));
-        const double fu = mul_rn(vyu, sub_rn(syu, tc[(iu - i) * tp]));
-        const double dy = div_rn(sub_rn(fd, fu), deny);
-        const double rnew = sub_rn(add_rn(add_rn(dx, dy), dh), sm);
+        // all global loads first: {surf, velx} / {surf, vely} / {dhdt, smb} pairs are one 16 B load each
+        const double2 xr = __ldg(d.sv + r + jr), xl = __ldg(d.sv + r + jl);
+        const double2 yd = __ldg(d.sy + (int64_t)id * W + j), yu = __ldg(d.sy + (int64_t)iu * W + j);
+        const double2 hs = __ldg(d.ds + r + j);
+        const double sc0 = __ldg(d.surf + r + j);
+        const uint8_t fl = __ldg(d.flags + r + j);
+        const double rold = __ldcg(mcres + r + j);
+        const double fr = mul_rn(xr.y, sub_rn(xr.x, tc[jr - j]));
+        const double fl_ = mul_rn(xl.y, sub_rn(xl.x, tc[jl - j]));
+        const double dx = div_const(sub_rn(fr, fl_), denx, rdx);
+        const double fd = mul_rn(yd.y, sub_rn(yd.x, tc[(id - i) * tp]));
+        const double fu = mul_rn(yu.y, sub_rn(yu.x, tc[(iu - i) * tp]));
+        const double dy = div_const(sub_rn(fd, fu), deny, rdy);
+        const double rnew = sub_rn(add_rn(add_rn(dx, dy), hs.x), hs.y);
         newres[e] = rnew;
         if (fl & FLAG_MC) {
             if (rnew == rnew && rold == rold) delta += (rnew - rold) * (rnew + rold);
@@ -610,6 +651,8 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
                long long* phase_acc) {
     __shared__ double scratch[40];
     __shared__ StepScalars sc;
+    __shared__ GmcPair s_pair;
+    __shared__ StepTables s_tab;
     double* buf = reinterpret_cast<double*>(gmc_smem);
     const int c = blockIdx.x;
     const int64_t plane = (int64_t)d.H * d.W;
@@ -626,41 +669,50 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
         const uint64_t it = iter0 + (uint64_t)k;
         const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
         if (resync_every > 0 && it % (uint64_t)resync_every == 0) ssq = resync_ssq(d, mcres, scratch);
-        if (threadIdx.x == 0) {
-            const GmcFieldModel& fm = d.fm;
-            // RandField stream: block size, scale, nugget, range(s)                   MCMC.py:755, 200-207
-            const uint4 r0 = rng(0u, it_lo, it_hi, GMC_STREAM_RF_SCALARS);
-            const uint4 r1 = rng(1u, it_lo, it_hi, GMC_STREAM_RF_SCALARS);
-            sc.pair = (int)bounded_u64(r0.x, r0.y, (uint64_t)d.n_pairs);
-            sc.scale = div_rn(add_rn(fm.scale_min, mul_rn(sub_rn(fm.scale_max, fm.scale_min), u01_halfopen(r0.z, r0.w))), 3.0);
-            sc.nug = add_rn(0.0, mul_rn(fm.nugget_max, u01_halfopen(r1.x, r1.y)));
-            sc.range_x = add_rn(fm.range_min_x, mul_rn(sub_rn(fm.range_max_x, fm.range_min_x), u01_halfopen(r1.z, r1.w)));
-            if (fm.isotropic) sc.range_y = sc.range_x;
-            else {
-                const uint4 r2 = rng(2u, it_lo, it_hi, GMC_STREAM_RF_SCALARS);
-                sc.range_y = add_rn(fm.range_min_y, mul_rn(sub_rn(fm.range_max_y, fm.range_min_y), u01_halfopen(r2.x, r2.y)));
+        if (threadIdx.x < 32) {
+            // the five Philox blocks of the step's scalars are drawn by five lanes in parallel, then gathered by lane 0
+            const int l = threadIdx.x;
+            uint4 r = make_uint4(0, 0, 0, 0);
+            if (l < 5) r = rng(l < 3 ? (uint32_t)l : (uint32_t)(l - 3), it_lo, it_hi, l < 3 ? GMC_STREAM_RF_SCALARS : GMC_STREAM_CHAIN);
+            uint4 g[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k)
+                g[k] = make_uint4(__shfl_sync(0xffffffffu, r.x, k), __shfl_sync(0xffffffffu, r.y, k),
+                                  __shfl_sync(0xffffffffu, r.z, k), __shfl_sync(0xffffffffu, r.w, k));
+            if (l == 0) {
+                const GmcFieldModel& fm = d.fm;
+                const uint4 r0 = g[0], r1 = g[1], r2 = g[2], c0 = g[3], c1 = g[4];
+                // RandField stream: block size, scale, nugget, range(s)                   MCMC.py:755, 200-207
+                sc.pair = (int)bounded_u64(r0.x, r0.y, (uint64_t)d.n_pairs);
+                sc.scale = div_rn(add_rn(fm.scale_min, mul_rn(sub_rn(fm.scale_max, fm.scale_min), u01_halfopen(r0.z, r0.w))), 3.0);
+                sc.nug = add_rn(0.0, mul_rn(fm.nugget_max, u01_halfopen(r1.x, r1.y)));
+                sc.range_x = add_rn(fm.range_min_x, mul_rn(sub_rn(fm.range_max_x, fm.range_min_x), u01_halfopen(r1.z, r1.w)));
+                if (fm.isotropic) sc.range_y = sc.range_x;
+                else sc.range_y = add_rn(fm.range_min_y, mul_rn(sub_rn(fm.range_max_y, fm.range_min_y), u01_halfopen(r2.x, r2.y)));
+                // chain stream: block centre (uniform over the allowed cells) and the acceptance uniform   MCMC.py:1253-1261, 1336
+                if (d.n_centre_cells > 0) {
+                    const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
+                    sc.ix = cell / d.W;
+                    sc.iy = cell - sc.ix * d.W;
+                } else {
+                    sc.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
+                    sc.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
+                }
+                sc.u = u01_halfopen(c1.x, c1.y);
+                s_pair = d.pairs[sc.pair];             // one trip: sizes, table offsets and both FFT plans
+                sc.h = s_pair.h;
+                sc.w = s_pair.w;
+                block_window(sc, d.H, d.W);
+                sc.spec = make_spec(fm, sc.range_x, sc.range_y);
             }
-            // chain stream: block centre (uniform over the allowed cells) and the acceptance uniform   MCMC.py:1253-1261, 1336
-            const uint4 c0 = rng(0u, it_lo, it_hi, GMC_STREAM_CHAIN);
-            if (d.n_centre_cells > 0) {
-                const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
-                sc.ix = cell / d.W;
-                sc.iy = cell - sc.ix * d.W;
-            } else {
-                sc.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
-                sc.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
-            }
-            const uint4 c1 = rng(1u, it_lo, it_hi, GMC_STREAM_CHAIN);
-            sc.u = u01_halfopen(c1.x, c1.y);
-            sc.h = d.pairs[sc.pair].h;
-            sc.w = d.pairs[sc.pair].w;
-            block_window(sc, d.H, d.W);
         }
         __syncthreads();
-        prefetch_block(sc, d.H, d.W, bed, mcres);
+        stage_tables(d, s_pair, s_tab);
+        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off);
+        __syncthreads();
         pc.mark(0);
-        const FieldView fv = synth_field<false>(d, buf, scratch, sc.pair, sc.scale, sc.nug, sc.range_x, sc.range_y, rng, it_lo,
-                                                it_hi, nullptr, nullptr, nullptr, true, pc);
+        const FieldView fv = synth_field<false>(d, buf, scratch, s_pair, s_tab, sc.scale, sc.nug, sc.spec, rng, it_lo, it_hi,
+                                                nullptr, nullptr, nullptr, true, pc);
         // tile after the field; the new residuals reuse the field's storage once the tile is built (f is dead by then)
         step_tail<false>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
                          nullptr, pc);
@@ -697,6 +749,7 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS)
     __syncthreads();
     double ssq = ssq_all[c];
     const Philox rng(0ull);
+    stage_block_async(sc, d.H, d.W, bed_all + c * plane, mcres_all + c * plane, buf + (int64_t)hmax * wmax);
     FieldView fv = {};
     PhaseClock pc;
     pc.acc = nullptr;
@@ -717,21 +770,30 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
                  const double* __restrict__ z_im, const double* __restrict__ z_nug, const uint64_t* __restrict__ seeds,
                  uint64_t iter, int apply_taper, double* __restrict__ f_out, int64_t stride) {
     __shared__ double scratch[40];
+    __shared__ GmcPair s_pair;
+    __shared__ StepTables s_tab;
     double* buf = reinterpret_cast<double*>(gmc_smem);
     const int i = blockIdx.x;
     const int p = pair[i];
+    if (threadIdx.x == 0) s_pair = d.pairs[p];
+    __syncthreads();
+    stage_tables(d, s_pair, s_tab);
+    __syncthreads();
     const Philox rng(INJECT ? 0ull : seeds[i]);
     const uint32_t it_lo = (uint32_t)iter, it_hi = (uint32_t)(iter >> 32);
     PhaseClock pc;
     pc.acc = nullptr;
-    const FieldView fv = synth_field<INJECT>(d, buf, scratch, p, scale[i], nug[i], range_x[i], range_y[i], rng, it_lo, it_hi,
+    const SpecParams sp = make_spec(d.fm, range_x[i], range_y[i]);
+    const FieldView fv = synth_field<INJECT>(d, buf, scratch, s_pair, s_tab, scale[i], nug[i], sp, rng, it_lo, it_hi,
                                              INJECT ? z_re + i * stride : nullptr, INJECT ? z_im + i * stride : nullptr,
                                              INJECT ? z_nug + i * stride : nullptr, apply_taper != 0, pc);
-    const int h = d.pairs[p].h, w = d.pairs[p].w;
+    const int h = s_pair.h, w = s_pair.w;
     const FastDiv dw(w);
     for (int e = threadIdx.x; e < h * w; e += GMC_STEP_THREADS) {
         const int y = dw.div(e), x = e - y * w;
-        f_out[i * stride + e] = field_value<INJECT>(fv, y, x, rng, it_lo, it_hi);
+        double f = field_value<INJECT>(fv, y, x, rng, it_lo, it_hi);
+        if (fv.taper) f = mul_rn(f, __ldg(fv.taper + e));                               // MCMC.py:778
+        f_out[i * stride + e] = f;
     }
 }
 
