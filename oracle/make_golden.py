@@ -34,7 +34,8 @@ def quiet(fn, *a, **k):
 
 # ---- the named trajectory cases: shared with tests/cases.py so oracle and reference see the same inputs ----
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from cases import TRAJECTORY_CASES, FIELD_CASES, residual_case_inputs, build_case_grids   # noqa: E402
+from cases import (TRAJECTORY_CASES, FIELD_CASES, SGS_CASES, residual_case_inputs, build_case_grids,   # noqa: E402
+                   build_sgs_inputs)
 
 
 def reference_chain(case):
@@ -64,8 +65,36 @@ def reference_chain(case):
                 edge_mask0=rf.edge_masks[0], edge_mask_last=rf.edge_masks[-1], pairs=rf.pairs)
 
 
+def reference_sgs_chain(case):
+    g = build_sgs_inputs(case)
+    ch = quiet(MCMC.chain_sgs, g["xx"], g["yy"], g["bed_init"], g["surf"], g["velx"], g["vely"], g["dhdt"], g["smb"],
+               g["cond_bed"], g["data_mask"], g["grounded_ice_mask"], g["resolution"])
+    quiet(ch.set_update_region, True, g["highvel_mask"])
+    ch.set_loss_type(sigma_mc=case["sigma_mc"], massConvInRegion=True)
+    ch.set_block_sizes(*case["blocks"])
+    ch.set_normal_transformation(g.get("nst"), do_transform=case["transform"])
+    ch.set_trend(g["trend"], detrend_map=case["detrend"])
+    v = case["vario"]
+    quiet(ch.set_variogram, v["vtype"], v["range"], v["sill"], v["nugget"], isotropic=v["isotropic"],
+          vario_smoothness=v["smoothness"], vario_azimuth=v["azimuth"])
+    quiet(ch.set_sgs_param, case["neighbors"], case["radius"])
+    ch.set_random_generator(case["seed"])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = quiet(ch.run, case["n_iter"], only_save_last_bed=True, info_per_iter=10 ** 9, plot=False, progress_bar=False)
+    bed, loss_mc, loss_data, loss, steps, resampled, blocks = out
+    return dict(bed=bed, loss_mc=loss_mc, loss_data=loss_data, loss=loss, steps=steps, resampled_times=resampled, blocks=blocks)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+
+    # (4) small-scale SGS chain trajectories
+    for name, case in SGS_CASES.items():
+        out = reference_sgs_chain(case)
+        np.savez_compressed(os.path.join(OUT, f"sgs_{name}.npz"), **out)
+        print(f"sgs_{name}: final loss {out['loss'][-1]!r}, acceptance {out['steps'].mean():.3f}")
 
     # (1) residual + loss known answers
     ri = residual_case_inputs()

@@ -74,3 +74,41 @@ def residual_case_inputs() -> dict:
     mask[5, 6] = 1
     return dict(xx=xx, yy=yy, bed=bed, surf=surf, velx=velx, vely=vely, dhdt=dhdt, smb=smb, mask=mask,
                 resolution=res, sigma_mc=2.5)
+
+
+# ---- small-scale SGS chain cases (chain_sgs.run, MCMC.py:1599) ------------------------------------------------------
+SGS_CASES = {
+    # tutorial-like: detrended + normal-score transformed bed, Matern variogram, ordinary kriging with octant search
+    "matern_nst": dict(H=60, W=64, n_iter=60, seed=17, sigma_mc=1.5, blocks=(4, 10, 4, 10), neighbors=16, radius=5e3,
+                       vario=dict(vtype="Matern", range=3000.0, sill=1.0, nugget=0.0, isotropic=True, smoothness=1.2259,
+                                  azimuth=None),
+                       transform=True, detrend=True, n_quantiles=500),
+    # raw bed (no transform, no trend), anisotropic exponential variogram, one neighbour per octant, thin ice (guard fires)
+    "expo_raw": dict(H=48, W=56, n_iter=60, seed=23, sigma_mc=20.0, blocks=(3, 9, 5, 8), neighbors=8, radius=4e3,
+                     vario=dict(vtype="Exponential", range=[4000.0, 2500.0], sill=900.0, nugget=0.0, isotropic=False,
+                                smoothness=None, azimuth=30.0),
+                     transform=False, detrend=False, thin=True),
+}
+
+
+def build_sgs_inputs(case: dict) -> dict:
+    """Grids + trend + fitted normal-score tables for an SGS case (tables come from sklearn, as in the tutorials)."""
+    from scipy.ndimage import gaussian_filter
+    g = syn.make_grids(case["H"], case["W"])
+    g = dict(g)
+    if case.get("thin"):
+        g["surf"] = g["bed0"] + 60.0 + 10.0 * np.sin(g["xx"] / 7e3)
+    # rough initial bed so the residual is informative
+    rng = np.random.default_rng(99)
+    g["bed_init"] = g["bed0"] + gaussian_filter(rng.standard_normal(g["bed0"].shape), 2.0) * 30.0
+    g["cond_bed"] = np.where(g["data_mask"] == 1, g["bed_init"], np.nan)
+    g["trend"] = gaussian_filter(g["bed_init"], 5.0) if case["detrend"] else None
+    g["quantiles"] = g["references"] = None
+    if case["transform"]:
+        from sklearn.preprocessing import QuantileTransformer
+        base = g["bed_init"] - (g["trend"] if case["detrend"] else 0.0)
+        nst = QuantileTransformer(n_quantiles=case["n_quantiles"], output_distribution="normal", subsample=None,
+                                  random_state=0).fit(base.reshape(-1, 1))
+        g["nst"] = nst
+        g["quantiles"], g["references"] = nst.quantiles_[:, 0].copy(), nst.references_.copy()
+    return g
