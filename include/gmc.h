@@ -132,6 +132,46 @@ GMC_API int gmc_run(gmc_ctx* ctx, double* bed, double* mcres, double* ssq, const
             double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache, int64_t cache_stride, int64_t cache_offset,
             int32_t* resampled, int resync_every, int C, void* stream);
 
+/* ---- S1-S5: small-scale chain (block re-simulation by SGS) ---------------------------------------------------- */
+
+/* Tables of the SGS chain (chain_sgs setters, MCMC.py:1465-1597).  All pointers "any" (host or device), copied.
+ *   trend [H][W] or NULL          : set_trend (MCMC.py:1481-1496); the chain state is bed - trend
+ *   zcond [H][W]                  : normal-scored conditioning data, NaN where none (MCMC.py:1653-1661)
+ *   grounded [H][W] u8            : grounded_ice_mask of the full-grid thickness guard (MCMC.py:1789-1795)
+ *   quantiles, references [n_q]   : QuantileTransformer.quantiles_[:,0], references_ (NULL/NULL: do_transform=False)
+ *   oct_off [8][lmax][2] i16, oct_cnt [8] : for octant b = -4..3 of neighbors.py:52-60 the window offsets (di, dj) with
+ *                                   distance < radius, sorted by (distance, di, dj); hw = window half width in cells
+ *   num_points                    : set_sgs_param neighbours (num_points//8 per octant)
+ *   lut [(4hw+1)][(4hw+1)]        : covariance of the offset (di, dj), di,dj in [-2hw, 2hw] (covariance.py models)
+ *   sill; block sizes             : variogram sill; set_block_sizes (sizes drawn from [min, max), MCMC.py:1755-1756) */
+GMC_API int gmc_sgs_setup(gmc_ctx* ctx, const double* trend, const double* zcond, const uint8_t* grounded,
+                          const double* quantiles, const double* references, int n_quantiles, const int16_t* oct_off,
+                          const int32_t* oct_cnt, int lmax, int hw, int num_points, const double* lut, double sill,
+                          int block_min_x, int block_max_x, int block_min_y, int block_max_y);
+
+/* QuantileTransformer(output_distribution='normal').transform / inverse_transform of n values (dev), S5. */
+GMC_API int gmc_sgs_transform(gmc_ctx* ctx, const double* in, double* out, int64_t n, int inverse, void* stream);
+
+/* Chain state from C full beds (dev [C][H][W]): bedc = bed - trend, z = normal score of bedc, mcres/ssq = residual and
+ * nansum of bedc + trend, nviol[C] = cells violating the thickness guard.  scratch_full: dev [C][H][W] work array.
+ * MCMC.py:1636-1669. */
+GMC_API int gmc_sgs_init(gmc_ctx* ctx, const double* bed, double* bedc, double* z, double* mcres, double* ssq, int32_t* nviol,
+                         double* scratch_full, int C, void* stream);
+
+/* One chain_sgs.run loop body (MCMC.py:1747-1829) for C chains with every random input injected:
+ *   centre [C][2] i32 (indexx, indexy); block_size [C][2] i32; path [C][path_stride] i32 = the shuffled visiting order
+ *   as block-local cell indices (row * block_width + col); znorm [C][path_stride] unit normals by path position; u [C].
+ *   err_flag (dev i32, may be NULL) is OR-ed with 1 if a node found no neighbour inside the search radius. */
+GMC_API int gmc_sgs_step_injected(gmc_ctx* ctx, double* bedc, double* z, double* mcres, double* ssq, int32_t* nviol,
+                                  const int32_t* centre, const int32_t* block_size, const int32_t* path, const double* znorm,
+                                  int64_t path_stride, const double* u, uint8_t* accepted_out, double* loss_out,
+                                  double* loss_next_out, int32_t* resampled, int32_t* err_flag, int C, void* stream);
+
+/* n_steps free-running SGS iterations for C chains (device Philox: centre, block size, path permutation, normals, u). */
+GMC_API int gmc_sgs_run(gmc_ctx* ctx, double* bedc, double* z, double* mcres, double* ssq, int32_t* nviol, const uint64_t* seeds,
+                        uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache,
+                        int64_t cache_stride, int64_t cache_offset, int32_t* resampled, int32_t* err_flag, int C, void* stream);
+
 /* ---- ensemble statistics (new) ---------------------------------------------------------------- */
 
 /* Local part of the posterior mean/variance: sum_out[H][W] = sum_c (bed_c - ref), sumsq_out = sum_c (bed_c - ref)^2. */

@@ -465,6 +465,247 @@ class chain_crf(chain):
         return outl
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# chain_sgs                                                                                  reference MCMC.py:1445-1911
+# ------------------------------------------------------------------------------------------------------------------
+class chain_sgs(chain):
+    """Small-scale chain: block re-simulation by Sequential Gaussian Simulation (reference MCMC.py:1445).  Same setters
+    and `run` signature/return tuple; every per-node operation (octant search, kriging solve, normal-score transform,
+    residual, loss, Metropolis) runs in kernel K6 (csrc/sgs.cu)."""
+
+    def __init_func__(self):
+        print("before running the chain, please set where the block update will be using the object's function "
+              "set_update_in_region(region_mask) and set_update_region(update_in_region)")
+        print("please also set up the sgs parameters using set_sgs_param(self, block_size, sgs_param)")
+        print("then please set up the loss function using either set_loss_type or set_loss_func")
+
+    def set_normal_transformation(self, nst_trans, do_transform=True):
+        self.do_transform = do_transform
+        self.nst_trans = nst_trans if do_transform else None
+        self._ctx = None
+
+    def set_trend(self, trend=None, detrend_map=True):
+        if detrend_map == True:  # noqa: E712
+            if len(trend) != len(self.xx) or trend.shape != self.xx.shape:
+                raise ValueError("if detrend_map is set to True, then the trend of the topography, which is a 2D numpy array, must be provided")
+            self.trend = trend
+        else:
+            self.trend = None
+        self.detrend_map = detrend_map
+        self._ctx = None
+
+    def set_variogram(self, vario_type, vario_range, vario_sill, vario_nugget, isotropic=True, vario_smoothness=None,
+                      vario_azimuth=None):
+        if vario_type in ("Gaussian", "Exponential", "Spherical"):
+            print("the variogram is set to type", vario_type)
+        elif vario_type == "Matern":
+            if (vario_smoothness is None) or (vario_smoothness <= 0):
+                raise ValueError("vario_smoothness argument should be a positive float when the vario_type is Matern")
+            print("the variogram is set to type", vario_type)
+        else:
+            raise ValueError("vario_type argument should be one of the following: Gaussian, Exponential, Spherical, or Matern")
+        self.vario_type = vario_type
+        if isotropic:
+            self.vario_param = [0, vario_nugget, vario_range, vario_range, vario_sill, vario_type, vario_smoothness]
+        else:
+            if len(vario_range) == 2:
+                print("set to anistropic variogram with major range and minor range to be ", vario_range)
+                self.vario_param = [vario_azimuth, vario_nugget, vario_range[0], vario_range[1], vario_sill, vario_type,
+                                    vario_smoothness]
+            else:
+                raise ValueError("vario_range need to be a list with two floats to specifying for major range and minor range "
+                                 "of the variogram when isotropic is set to False")
+        self._ctx = None
+
+    def set_sgs_param(self, sgs_num_nearest_neighbors, sgs_searching_radius, sgs_rand_dropout_on=False, dropout_rate=0):
+        if sgs_rand_dropout_on == False:  # noqa: E712
+            dropout_rate = 0
+            print("because the sgs_rand_dropout_on is set to False, the dropout_rate is automatically set to 0")
+        self.sgs_param = [sgs_num_nearest_neighbors, sgs_searching_radius, sgs_rand_dropout_on, dropout_rate]
+        self._ctx = None
+
+    def set_block_sizes(self, block_min_x, block_max_x, block_min_y, block_max_y):
+        self.block_min_x, self.block_max_x = block_min_x, block_max_x
+        self.block_min_y, self.block_max_y = block_min_y, block_max_y
+        self._ctx = None
+
+    # ---- device context ------------------------------------------------------------------------------------------
+    def _vario_dict(self):
+        """The dict the reference hands to sgs() (MCMC.py:1682-1702)."""
+        p = self.vario_param
+        v = dict(azimuth=p[0], nugget=p[1], major_range=p[2], minor_range=p[3], sill=p[4], vtype=p[5])
+        if p[5] == "Matern":
+            v["s"] = p[6]
+        return v
+
+    def _sgs_context(self, max_chains, device=None):
+        from . import sgs_tables as T
+        key = ("sgs", max_chains, str(device))
+        if self._ctx is not None and self._ctx_key == key:
+            return self._ctx
+        H, W = self.xx.shape
+        region = self._binary(self.region_mask, "region_mask")
+        centre = np.flatnonzero(region.ravel() == 1).astype(np.int32)        # the reference always samples inside region_mask
+        if centre.size == 0:
+            raise ValueError("region_mask selects no cell: the reference would loop forever drawing a block centre")
+        ctx = Context(H, W, max_chains, device)
+        ones = np.ones((H, W), dtype=np.uint8)
+        ctx.set_static(self.surf, self.velx, self.vely, self.dhdt, self.smb, ones, self._binary(self.mc_region_mask, "mc_region_mask"),
+                       centre, None, self.resolution, self.sigma_mc)
+        dx, dy = T.grid_steps(np.asarray(self.xx), np.asarray(self.yy))
+        vario = self._vario_dict()
+        off, cnt, hw = T.octant_stencil(dx, dy, self.sgs_param[1])
+        lut = T.covariance_lut(dx, dy, hw, vario)
+        trend = np.asarray(self.trend, dtype=np.float64) if self.detrend_map else None
+        cond_c = np.asarray(self.cond_bed, dtype=np.float64) - (trend if trend is not None else 0.0)
+        if self.do_transform:
+            zcond = self.nst_trans.transform(cond_c.reshape(-1, 1)).reshape(H, W)     # MCMC.py:1653-1661
+            quant, refs = self.nst_trans.quantiles_[:, 0], self.nst_trans.references_
+            if getattr(self.nst_trans, "output_distribution", "normal") != "normal":
+                raise NotImplementedError("only QuantileTransformer(output_distribution='normal') is supported")
+        else:
+            zcond, quant, refs = cond_c, None, None
+        ctx.sgs_setup(trend, zcond, self.grounded_ice_mask, quant, refs, off, cnt, hw, self.sgs_param[0], lut, vario["sill"],
+                      (self.block_min_x, self.block_max_x, self.block_min_y, self.block_max_y))
+        self._ctx, self._ctx_key = ctx, key
+        return ctx
+
+    def run(self, n_iter, only_save_last_bed=False, info_per_iter=100, plot=True, progress_bar=True, *, replay=None):
+        """n_iter block re-simulation proposals on the GPU; the reference's return tuple (MCMC.py:1599, 1897-1911).
+
+        replay: optional sequence of dict(idx_x, idx_y, bsx, bsy, path[n,2], z[n], u) — the recorded random inputs of a
+        reference/oracle run, replayed through gmc_sgs_step_injected."""
+        if not hasattr(self, "rng_seed_int"):
+            self.set_random_generator(None)
+        H, W = self.xx.shape
+        batch = SgsBatch(self, np.ascontiguousarray(self.initial_bed, dtype=np.float64)[None], [philox_key(self.rng_seed_int)],
+                         iter0=getattr(self, "_philox_iter_sgs", 0))
+        loss_cache, step_cache = np.zeros(n_iter), np.zeros(n_iter)
+        blocks_cache = np.full((n_iter, 4), np.nan)
+        bed_cache = None if only_save_last_bed else np.zeros((n_iter, H, W))
+        sample_values = sample_ij = None
+        if self.sample_loc is not None:
+            sample_values = np.zeros((self.sample_loc.shape[0], n_iter))
+            sample_ij = np.zeros(self.sample_loc.shape, dtype=np.int64)
+            for k in range(self.sample_loc.shape[0]):
+                si, sj = np.where((self.xx == self.sample_loc[k, 0]) & (self.yy == self.sample_loc[k, 1]))
+                sample_ij[k, :] = [int(si[0]), int(sj[0])]
+        per_step = (bed_cache is not None) or (sample_values is not None) or (replay is not None)
+        done = 0
+        while done < n_iter:
+            if replay is not None:
+                p = replay[done]
+                acc, loss_now = batch.step_injected([p])
+                loss_cache[done], step_cache[done] = loss_now[0], acc[0]
+                blocks_cache[done] = [p["idx_x"], p["idx_y"], p["bsx"], p["bsy"]]
+                n = 1
+            else:
+                n = 1 if per_step else n_iter - done
+                lc, st, bl = batch.advance(n)
+                loss_cache[done:done + n], step_cache[done:done + n], blocks_cache[done:done + n] = lc[0], st[0], bl[0]
+            done += n
+            if per_step and (bed_cache is not None or sample_values is not None):
+                bed_now = batch.beds(with_trend=True)[0]
+                if bed_cache is not None:
+                    bed_cache[done - 1] = bed_now
+                if sample_values is not None:
+                    sample_values[:, done - 1] = batch.beds(with_trend=False)[0][sample_ij[:, 0], sample_ij[:, 1]]
+        self._philox_iter_sgs = batch.iteration
+        last_bed = batch.beds(with_trend=True)[0]
+        resampled = batch.resampled_times()[0]
+        first = last_bed if only_save_last_bed else bed_cache
+        out = (first, loss_cache.copy(), np.zeros(n_iter), loss_cache, step_cache, resampled, blocks_cache)
+        batch.close()
+        return out + ((sample_values,) if sample_values is not None else ())
+
+
+class SgsBatch:
+    """Device-resident state of C small-scale chains: detrended bed, its normal score, residual, nansum, guard count."""
+
+    def __init__(self, chain_obj, initial_beds, keys, iter0=0, device=None):
+        import torch
+        self.torch = torch
+        beds = np.ascontiguousarray(initial_beds, dtype=np.float64)
+        if beds.ndim != 3 or beds.shape[1:] != chain_obj.xx.shape:
+            raise GmcShapeError(f"initial beds have shape {beds.shape}, expected [C,{chain_obj.xx.shape[0]},{chain_obj.xx.shape[1]}]")
+        self.C, self.H, self.W = beds.shape
+        self.chain = chain_obj
+        self.ctx = chain_obj._sgs_context(self.C, device)
+        dev = self.dev = self.ctx.device
+        full = torch.as_tensor(beds).to(dev)
+        self.bedc = torch.empty_like(full)
+        self.z = torch.empty_like(full)
+        self.mcres = torch.empty_like(full)
+        self.ssq = torch.empty(self.C, dtype=torch.float64, device=dev)
+        self.nviol = torch.zeros(self.C, dtype=torch.int32, device=dev)
+        self.resampled = torch.zeros(beds.shape, dtype=torch.int32, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seeds = keys_tensor(keys, dev)
+        self.iteration = int(iter0)
+        self.trend = None if not chain_obj.detrend_map else torch.as_tensor(np.ascontiguousarray(chain_obj.trend, dtype=np.float64)).to(dev)
+        scratch = torch.empty_like(full)
+        self.ctx.sgs_init(full, self.bedc, self.z, self.mcres, self.ssq, self.nviol, scratch)
+
+    def close(self):
+        self.bedc = self.z = self.mcres = self.resampled = None
+
+    def _check_err(self):
+        if int(self.err.item()) != 0:
+            raise GmcError("SGS: a node found no conditioned neighbour inside the search radius; the reference widens the "
+                           "radius by 100 km in that case (MCMC.py:149-155), which this kernel does not implement")
+
+    def loss(self):
+        den = self.torch.full_like(self.ssq, 2 * self.chain.sigma_mc ** 2)
+        return (self.ssq / den).cpu().numpy()
+
+    def beds(self, with_trend=True):
+        b = self.bedc + self.trend if (with_trend and self.trend is not None) else self.bedc
+        return b.cpu().numpy()
+
+    def resampled_times(self):
+        return self.resampled.cpu().numpy().astype(np.float64)
+
+    def advance(self, n_steps):
+        torch = self.torch
+        lc = torch.empty((self.C, n_steps), dtype=torch.float64, device=self.dev)
+        st = torch.empty((self.C, n_steps), dtype=torch.uint8, device=self.dev)
+        bl = torch.empty((self.C, n_steps, 4), dtype=torch.int32, device=self.dev)
+        self.ctx.sgs_run(self.bedc, self.z, self.mcres, self.ssq, self.nviol, self.seeds, self.iteration, n_steps, lc, st, bl, 0,
+                         self.resampled, self.err)
+        self.iteration += n_steps
+        self._check_err()
+        return lc.cpu().numpy(), st.cpu().numpy(), bl.cpu().numpy()
+
+    def step_injected(self, tapes):
+        """One step per chain from recorded inputs (dict(idx_x, idx_y, bsx, bsy, path[n,2] grid indices, z[n], u))."""
+        torch = self.torch
+        H, W = self.H, self.W
+        nmax = max(len(t["path"]) for t in tapes)
+        path = np.zeros((self.C, nmax), dtype=np.int32)
+        zn = np.zeros((self.C, nmax))
+        centre = np.zeros((self.C, 2), dtype=np.int32)
+        bs = np.zeros((self.C, 2), dtype=np.int32)
+        us = np.zeros(self.C)
+        for c, t in enumerate(tapes):
+            x0, x1 = max(0, int(t["idx_x"] - t["bsx"] / 2)), min(H, int(t["idx_x"] + t["bsx"] / 2))
+            y0, y1 = max(0, int(t["idx_y"] - t["bsy"] / 2)), min(W, int(t["idx_y"] + t["bsy"] / 2))
+            p = np.asarray(t["path"])
+            path[c, :len(p)] = (p[:, 0] - x0) * (y1 - y0) + (p[:, 1] - y0)
+            zn[c, :len(p)] = np.nan_to_num(np.asarray(t["z"], dtype=np.float64))
+            centre[c] = (t["idx_x"], t["idx_y"])
+            bs[c] = (t["bsx"], t["bsy"])
+            us[c] = t["u"]
+        dev = self.dev
+        acc = torch.empty(self.C, dtype=torch.uint8, device=dev)
+        loss = torch.empty(self.C, dtype=torch.float64, device=dev)
+        cu = lambda a: torch.as_tensor(a).to(dev)                                         # noqa: E731
+        self.ctx.sgs_step_injected(self.bedc, self.z, self.mcres, self.ssq, self.nviol, cu(centre), cu(bs), cu(path), cu(zn), cu(us),
+                                   acc, loss, None, self.resampled, self.err)
+        self.iteration += 1
+        self._check_err()
+        return acc.cpu().numpy().astype(bool), loss.cpu().numpy()
+
+
 class ChainBatch:
     """Device-resident state of C chains sharing one chain_crf configuration: bed[C,H,W], mcres[C,H,W], ssq[C]."""
 

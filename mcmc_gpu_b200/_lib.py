@@ -47,6 +47,12 @@ PROTOTYPES = {
                           C.c_int, C.c_int, _c_p]),
     "gmc_ensemble_moments": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_allreduce_moments": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "gmc_sgs_setup": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int, _c_p, _f64,
+                                C.c_int, C.c_int, C.c_int, C.c_int]),
+    "gmc_sgs_transform": (C.c_int, [_c_p, _c_p, _c_p, _i64, C.c_int, _c_p]),
+    "gmc_sgs_init": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
+    "gmc_sgs_step_injected": (C.c_int, [_c_p] * 10 + [_i64] + [_c_p] * 6 + [C.c_int, _c_p]),
+    "gmc_sgs_run": (C.c_int, [_c_p] * 7 + [_u64, C.c_int, _c_p, _c_p, _c_p, _i64, _i64, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_launch_count": (_i64, [_c_p]),
     "gmc_step_kernel_info": (C.c_int, [_c_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gmc_debug_phase_timing": (C.c_int, [_c_p, C.c_int, _c_p]),
@@ -226,6 +232,40 @@ class Context:
         check(self.lib.gmc_run(self._h, _ptr(bed), _ptr(mcres), _ptr(ssq), _ptr(seeds), int(iter0), int(n_steps),
                                _ptr(loss_cache), _ptr(step_cache), _ptr(blocks_cache), stride, int(cache_offset),
                                _ptr(resampled), int(resync_every), bed.shape[0], _stream()))
+
+    # ---- SGS chain -------------------------------------------------------------------------------------------
+    def sgs_setup(self, trend, zcond, grounded, quantiles, references, oct_off, oct_cnt, hw, num_points, lut, sill, blocks):
+        f64 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)          # noqa: E731
+        trend, zcond, quantiles, references, lut = f64(trend), f64(zcond), f64(quantiles), f64(references), f64(lut)
+        grounded = np.ascontiguousarray(np.asarray(grounded) == 1, dtype=np.uint8)
+        oct_off = np.ascontiguousarray(oct_off, dtype=np.int16)
+        oct_cnt = np.ascontiguousarray(oct_cnt, dtype=np.int32)
+        check(self.lib.gmc_sgs_setup(self._h, _ptr(trend), _ptr(zcond), _ptr(grounded), _ptr(quantiles), _ptr(references),
+                                     0 if quantiles is None else quantiles.size, _ptr(oct_off), _ptr(oct_cnt), oct_off.shape[1],
+                                     int(hw), int(num_points), _ptr(lut), float(sill), *[int(b) for b in blocks]))
+
+    def sgs_transform(self, x, out, inverse=False):
+        check(self.lib.gmc_sgs_transform(self._h, _ptr(x), _ptr(out), x.numel(), int(bool(inverse)), _stream()))
+
+    def sgs_init(self, bed, bedc, z, mcres, ssq, nviol, scratch):
+        check(self.lib.gmc_sgs_init(self._h, _ptr(bed), _ptr(bedc), _ptr(z), _ptr(mcres), _ptr(ssq), _ptr(nviol), _ptr(scratch),
+                                    bed.shape[0], _stream()))
+
+    def sgs_step_injected(self, bedc, z, mcres, ssq, nviol, centre, bs, path, znorm, u, accepted, loss, loss_next=None,
+                          resampled=None, err=None):
+        check(self.lib.gmc_sgs_step_injected(self._h, _ptr(bedc), _ptr(z), _ptr(mcres), _ptr(ssq), _ptr(nviol), _ptr(centre),
+                                             _ptr(bs), _ptr(path), _ptr(znorm), path.shape[1], _ptr(u), _ptr(accepted), _ptr(loss),
+                                             _ptr(loss_next), _ptr(resampled), _ptr(err), bedc.shape[0], _stream()))
+
+    def sgs_run(self, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache=None, step_cache=None, blocks_cache=None,
+                cache_offset=0, resampled=None, err=None):
+        stride = 0
+        for t in (loss_cache, step_cache, blocks_cache):
+            if t is not None:
+                stride = t.shape[1]
+        check(self.lib.gmc_sgs_run(self._h, _ptr(bedc), _ptr(z), _ptr(mcres), _ptr(ssq), _ptr(nviol), _ptr(seeds), int(iter0),
+                                   int(n_steps), _ptr(loss_cache), _ptr(step_cache), _ptr(blocks_cache), stride, int(cache_offset),
+                                   _ptr(resampled), _ptr(err), bedc.shape[0], _stream()))
 
     def ensemble_moments(self, bed, ref_bed, sum_out, sumsq_out):
         check(self.lib.gmc_ensemble_moments(self._h, _ptr(bed), _ptr(ref_bed), _ptr(sum_out), _ptr(sumsq_out),

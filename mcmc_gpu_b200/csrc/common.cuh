@@ -105,6 +105,9 @@ struct GmcDev {
     GmcFieldModel fm;
 };
 
+struct gmc_sgs_state;
+void gmc_sgs_destroy(struct gmc_ctx* c);
+
 struct gmc_ctx {
     int device;
     int H, W, max_chains;
@@ -131,6 +134,7 @@ struct gmc_ctx {
     int step_ctas_per_sm;
     int64_t launches;
     long long* d_phase;    // optional per-phase cycle counters of run_kernel (debug)
+    gmc_sgs_state* sgs;    // small-scale (SGS) chain tables, see sgs.cu
 };
 
 #define FLAG_GATE 1

@@ -62,6 +62,7 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->step_ctas_per_sm = 0;
     c->launches = 0;
     c->d_phase = nullptr;
+    c->sgs = nullptr;
     c->dev.H = H;
     c->dev.W = W;
     // loss partials: one per (chain, row-tile); sized for the residual kernel's tiling (residual.cu)
@@ -84,6 +85,7 @@ extern "C" int gmc_destroy(gmc_ctx* c) {
     cudaFree(c->d_ksq);
     cudaFree(c->d_edge_masks);
     cudaFree(c->d_phase);
+    gmc_sgs_destroy(c);
     delete c;
     return GMC_OK;
 }

@@ -1,0 +1,678 @@
+// sgs.cu — K6: the small-scale chain step (block re-simulation by Sequential Gaussian Simulation).
+//
+// Reference: chain_sgs.run loop body (MCMC.py:1747-1829), MCMC.sgs (MCMC.py:91-173), octant neighbour search
+// (gstatsim_custom/neighbors.py:4-64), ordinary kriging (gstatsim_custom/_krige.py:5-44), covariance models
+// (gstatsim_custom/covariance.py), sklearn QuantileTransformer column transform (MCMC.py:1767,1777).
+//
+// One CTA (256 threads = 8 warps = the 8 octants) owns one chain.  Per iteration:
+//   1. the block's cells are reset to the normal-scored radar values (NaN elsewhere) in shared memory;
+//   2. along the (injected or Philox-shuffled) path every unconditioned node is kriged: warp o walks octant o's offset
+//      list — offsets pre-sorted on the host by (distance, row-major position), so the first num_points/8 conditioned
+//      hits ARE the reference's argsort selection — the (n+1)x(n+1) ordinary-kriging system is assembled from a host-built
+//      covariance table over integer offsets (this is where scipy's Bessel-K Matern lives) and solved in shared memory
+//      (elimination without pivoting on the SPD block, two right-hand sides, Lagrange multiplier by Schur complement);
+//   3. the block is mapped back through the normal-score tables, the residual is recomputed on the block plus its
+//      one-cell ring (the reference recomputes the full grid: the result is identical, nothing else changed), the loss
+//      changes by that region's delta, the full-grid thickness guard is a running violation count, Metropolis decides.
+// Where the reference calls np.linalg.lstsq (SVD, minimum norm) we solve exactly; the systems are well conditioned
+// (cond ~1e4, |d est| <= 6e-13), parity is <= 1e-9 as for every floating-point result of this chain.
+#include "common.cuh"
+
+#define SGS_THREADS 256
+#define SGS_MAX_BLOCK 32          // largest block edge (cells)
+#define SGS_MAX_NEIGH 64          // largest num_points
+#define SGS_SIG_PITCH (SGS_MAX_NEIGH + 1)
+
+struct SgsDev {
+    const double* trend;          // [H][W] or nullptr
+    const double* zcond;          // [H][W] normal-scored radar values, NaN where none
+    const uint8_t* grounded;      // [H][W]
+    const double* quant;          // [nq] quantiles (nullptr: no transform)
+    const double* refs;           // [nq] references
+    int nq;
+    const int16_t* oct_off;       // [8][lmax][2] (di, dj), sorted by (distance, di, dj); octant b-(-4) of neighbors.py:54
+    const int32_t* oct_cnt;       // [8]
+    int lmax, hw, per_oct;        // per_oct = num_points // 8
+    const double* lut;            // [(4hw+1)][(4hw+1)] covariance of the offset (di, dj)
+    int lut_w;                    // 4hw+1
+    double sill;
+    int bmin_x, bmax_x, bmin_y, bmax_y;
+};
+
+struct gmc_sgs_state {
+    SgsDev dev;
+    bool ready;
+    void* owned[8];
+};
+
+// ---- normal-score transform (QuantileTransformer._transform_col, output_distribution='normal') ---------------------
+// np.interp(x, xp, fp): binary search + slope*(x - xp[j]) + fp[j]; clamped outside [xp[0], xp[n-1]]
+__device__ __forceinline__ double interp_tab(double x, const double* __restrict__ xp, const double* __restrict__ fp, int n,
+                                             bool negrev) {
+    // negrev: use the tables -xp[::-1], -fp[::-1] (second interpolation of the forward transform)
+    auto XP = [&](int k) { return negrev ? -xp[n - 1 - k] : xp[k]; };
+    auto FP = [&](int k) { return negrev ? -fp[n - 1 - k] : fp[k]; };
+    if (x <= XP(0)) return FP(0);
+    if (x >= XP(n - 1)) return FP(n - 1);
+    int lo = 0, hi = n - 1;                       // XP(lo) <= x < XP(hi)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (XP(mid) <= x) lo = mid;
+        else hi = mid;
+    }
+    const double slope = div_rn(sub_rn(FP(lo + 1), FP(lo)), sub_rn(XP(lo + 1), XP(lo)));
+    return add_rn(mul_rn(slope, sub_rn(x, XP(lo))), FP(lo));
+}
+
+__device__ __forceinline__ double nst_forward(const SgsDev& s, double x) {
+    if (!s.quant) return x;
+    if (x != x) return x;
+    const double lo_q = s.quant[0], hi_q = s.quant[s.nq - 1];
+    double y = 0.5 * (interp_tab(x, s.quant, s.refs, s.nq, false) - interp_tab(-x, s.quant, s.refs, s.nq, true));
+    if (x + 1e-7 > hi_q) y = 1.0;
+    if (x - 1e-7 < lo_q) y = 0.0;
+    double z = normcdfinv(y);
+    // clip_min = norm.ppf(1e-7 - spacing(1)), clip_max = norm.ppf(1 - (1e-7 - spacing(1)))  (not symmetric in floating point)
+    return fmin(fmax(z, -5.199337582605575), 5.19933758270342);
+}
+
+__device__ __forceinline__ double nst_inverse(const SgsDev& s, double z) {
+    if (!s.quant) return z;
+    if (z != z) return z;
+    const double p = normcdf(z);
+    double x = interp_tab(p, s.refs, s.quant, s.nq, false);
+    if (p + 1e-7 > 1.0) x = s.quant[s.nq - 1];
+    if (p - 1e-7 < 0.0) x = s.quant[0];
+    return x;
+}
+
+__global__ void sgs_transform_kernel(SgsDev s, const double* __restrict__ in, double* __restrict__ out, int64_t n, int inverse) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = inverse ? nst_inverse(s, in[k]) : nst_forward(s, in[k]);
+}
+
+// bedc = bed - trend;  z = forward(bedc);  nviol = #{grounded & surf - bed <= 0}
+__global__ void sgs_init_kernel(GmcDev d, SgsDev s, const double* __restrict__ bed, double* __restrict__ bedc,
+                                double* __restrict__ z, int32_t* __restrict__ nviol, int C) {
+    const int c = blockIdx.y;
+    const int64_t plane = (int64_t)d.H * d.W;
+    int local = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < plane; k += (int64_t)gridDim.x * blockDim.x) {
+        const double b = bed[c * plane + k];
+        const double bc = s.trend ? sub_rn(b, s.trend[k]) : b;
+        bedc[c * plane + k] = bc;
+        z[c * plane + k] = nst_forward(s, bc);
+        const double full = s.trend ? add_rn(bc, s.trend[k]) : bc;
+        if (s.grounded[k] == 1 && sub_rn(d.surf[k], full) <= 0.0) ++local;
+    }
+    if (local) atomicAdd(nviol + c, local);
+}
+
+// full bed = bedc + trend  (for the residual of the initial state)
+__global__ void sgs_fullbed_kernel(GmcDev d, SgsDev s, const double* __restrict__ bedc, double* __restrict__ full, int64_t n) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) full[k] = s.trend ? add_rn(bedc[k], s.trend[k % ((int64_t)d.H * d.W)]) : bedc[k];
+}
+
+// ---- the step -------------------------------------------------------------------------------------------------------
+struct SgsShared {
+    double blk_z[SGS_MAX_BLOCK * SGS_MAX_BLOCK];       // simulated normal scores of the block (NaN: not yet)
+    double cand[SGS_MAX_BLOCK * SGS_MAX_BLOCK];        // candidate detrended bed of the block
+    double newres[(SGS_MAX_BLOCK + 2) * (SGS_MAX_BLOCK + 2)];
+    double sig[(SGS_MAX_NEIGH) * SGS_SIG_PITCH];       // Sigma (row-major, pitch n+... fixed)
+    double rhs_a[SGS_MAX_NEIGH], rhs_b[SGS_MAX_NEIGH]; // right-hand sides rho and 1
+    double nval[SGS_MAX_NEIGH];
+    int16_t ndi[SGS_MAX_NEIGH], ndj[SGS_MAX_NEIGH];
+    int oct_n[8];
+    int path[SGS_MAX_BLOCK * SGS_MAX_BLOCK];
+    unsigned long long keys[SGS_MAX_BLOCK * SGS_MAX_BLOCK];
+    double scratch[40];
+    int ix, iy, bsx, bsy, x0, x1, y0, y1, accept, n_nb, err;
+    double u;
+};
+
+__device__ __forceinline__ double lut_cov(const SgsDev& s, int di, int dj) {
+    return __ldg(s.lut + (di + 2 * s.hw) * s.lut_w + (dj + 2 * s.hw));
+}
+
+template <bool INJECT>
+__device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, double* bedc, double* z, double* mcres, double& ssq,
+                             int& nviol, const int32_t* path_in, const double* zn_in, const Philox& rng, uint32_t it_lo,
+                             uint32_t it_hi, int32_t* resampled, double* loss_next_out) {
+    const int H = d.H, W = d.W, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int x0 = S.x0, x1 = S.x1, y0 = S.y0, y1 = S.y1;
+    const int bh = x1 - x0, bw = y1 - y0, nblk = bh * bw;
+    // (1) block <- normal-scored conditioning data (NaN where there is none)              MCMC.py:1771
+    for (int e = tid; e < nblk; e += SGS_THREADS) {
+        const int bi = e / bw, bj = e - bi * bw;
+        S.blk_z[e] = __ldg(s.zcond + (int64_t)(x0 + bi) * W + (y0 + bj));
+    }
+    // path: injected order, or a uniformly random permutation by sorting Philox keys         MCMC.py:125
+    if (INJECT) {
+        for (int e = tid; e < nblk; e += SGS_THREADS) S.path[e] = path_in[e];
+    } else {
+        int npad = 1;
+        while (npad < nblk) npad <<= 1;
+        for (int e = tid; e < npad; e += SGS_THREADS) {
+            unsigned long long k = ~0ull;
+            if (e < nblk) {
+                const uint4 r = rng((uint32_t)e, it_lo, it_hi, 5u);          // stream 5: path keys
+                k = ((((unsigned long long)r.x << 32) | r.y) & ~0x3ffull) | (unsigned long long)e;   // unique: index in low bits
+            }
+            S.keys[e] = k;
+        }
+        __syncthreads();
+        for (int k2 = 2; k2 <= npad; k2 <<= 1)                                 // bitonic sort, ascending
+            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+                for (int e = tid; e < npad; e += SGS_THREADS) {
+                    const int p = e ^ j2;
+                    if (p > e) {
+                        const unsigned long long a = S.keys[e], b = S.keys[p];
+                        const bool up = (e & k2) == 0;
+                        if ((a > b) == up) { S.keys[e] = b; S.keys[p] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int e = tid; e < nblk; e += SGS_THREADS) S.path[e] = (int)(S.keys[e] & 0x3ffull);
+    }
+    __syncthreads();
+
+    // (2) sequential simulation along the path                                              MCMC.py:130-169
+    for (int k = 0; k < nblk; ++k) {
+        const int node = S.path[k];
+        const double cur = S.blk_z[node];
+        if (cur == cur) continue;                       // conditioned (radar value): uniform across the CTA
+        const int bi = node / bw, bj = node - bi * bw;
+        const int i = x0 + bi, j = y0 + bj;
+        // (a) octant search: warp `wid` owns octant wid (b = wid - 4)                           neighbors.py:52-60
+        {
+            const int16_t* off = s.oct_off + (int64_t)wid * s.lmax * 2;
+            const int cnt = __ldg(s.oct_cnt + wid);
+            int found = 0;
+            for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
+                const int t = base + lane;
+                bool ok = false;
+                int di = 0, dj = 0;
+                double v = 0.0;
+                if (t < cnt) {
+                    di = off[2 * t];
+                    dj = off[2 * t + 1];
+                    const int ci = i + di, cj = j + dj;
+                    if (ci >= 0 && ci < H && cj >= 0 && cj < W) {
+                        if (ci >= x0 && ci < x1 && cj >= y0 && cj < y1) v = S.blk_z[(ci - x0) * bw + (cj - y0)];
+                        else v = __ldcg(z + (int64_t)ci * W + cj);
+                        ok = (v == v);
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const int rank = found + __popc(m & ((1u << lane) - 1u));
+                if (ok && rank < s.per_oct) {
+                    const int slot = wid * s.per_oct + rank;
+                    S.ndi[slot] = (int16_t)di;
+                    S.ndj[slot] = (int16_t)dj;
+                    S.nval[slot] = v;
+                }
+                found += __popc(m);
+            }
+            if (lane == 0) S.oct_n[wid] = min(found, s.per_oct);
+        }
+        __syncthreads();
+        // (b) compact the octant lists (octant order -4..3, each sorted by distance) -> n neighbours
+        int n = 0, start[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+            start[o] = n;
+            n += S.oct_n[o];
+        }
+        if (n == 0) {                                   // the reference would widen the radius by 100 km (MCMC.py:149-155)
+            if (tid == 0) S.err = 1;
+            if (tid == 0) S.blk_z[node] = 0.0;
+            __syncthreads();
+            continue;
+        }
+        // read my neighbour (threads < 64 hold one slot each), then write it to its compacted position
+        int mdi = 0, mdj = 0, dst = -1;
+        double mval = 0.0;
+        if (tid < 8 * s.per_oct) {
+            const int o = tid / s.per_oct, r = tid - o * s.per_oct;
+            if (r < S.oct_n[o]) {
+                mdi = S.ndi[tid];
+                mdj = S.ndj[tid];
+                mval = S.nval[tid];
+                dst = start[o] + r;
+            }
+        }
+        __syncthreads();
+        if (dst >= 0) {
+            S.ndi[dst] = (int16_t)mdi;
+            S.ndj[dst] = (int16_t)mdj;
+            S.nval[dst] = mval;
+        }
+        __syncthreads();
+        // (c) assemble Sigma (n x n), rho and the ones vector                                   _krige.py:20-33
+        for (int t = tid; t < n * n; t += SGS_THREADS) {
+            const int a = t / n, b = t - a * n;
+            S.sig[a * SGS_SIG_PITCH + b] = lut_cov(s, S.ndi[a] - S.ndi[b], S.ndj[a] - S.ndj[b]);
+        }
+        if (tid < n) {
+            S.rhs_a[tid] = lut_cov(s, -S.ndi[tid], -S.ndj[tid]);
+            S.rhs_b[tid] = 1.0;
+        }
+        __syncthreads();
+        // rho is needed again for the variance: keep a register copy in the first n threads
+        const double rho_keep = (tid < n) ? S.rhs_a[tid] : 0.0;
+        // (d) elimination without pivoting (SPD block), both right-hand sides carried along
+        for (int p = 0; p < n - 1; ++p) {
+            const double inv = 1.0 / S.sig[p * SGS_SIG_PITCH + p];
+            const int m = n - 1 - p;                    // rows below the pivot
+            for (int t = tid; t < m * (m + 2); t += SGS_THREADS) {
+                const int r = p + 1 + t / (m + 2), cidx = t % (m + 2);
+                const double f = S.sig[r * SGS_SIG_PITCH + p] * inv;
+                if (cidx < m) {
+                    const int cc = p + 1 + cidx;
+                    S.sig[r * SGS_SIG_PITCH + cc] -= f * S.sig[p * SGS_SIG_PITCH + cc];
+                } else if (cidx == m) S.rhs_a[r] -= f * S.rhs_a[p];
+                else S.rhs_b[r] -= f * S.rhs_b[p];
+            }
+            __syncthreads();
+        }
+        // back substitution by warp 0 (upper triangle), two right-hand sides
+        if (wid == 0) {
+            for (int r = n - 1; r >= 0; --r) {
+                double sa = 0.0, sb = 0.0;
+                for (int cc = r + 1 + lane; cc < n; cc += 32) {
+                    const double a = S.sig[r * SGS_SIG_PITCH + cc];
+                    sa += a * S.rhs_a[cc];
+                    sb += a * S.rhs_b[cc];
+                }
+                sa = warp_sum(sa);
+                sb = warp_sum(sb);
+                if (lane == 0) {
+                    const double dg = S.sig[r * SGS_SIG_PITCH + r];
+                    S.rhs_a[r] = (S.rhs_a[r] - sa) / dg;
+                    S.rhs_b[r] = (S.rhs_b[r] - sb) / dg;
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // (e) Lagrange multiplier, weights, estimate and variance (warp 0)                        _krige.py:36-43
+        if (wid == 0) {
+            double s1a = 0.0, s1b = 0.0, sv = 0.0;
+            for (int t = lane; t < n; t += 32) {
+                s1a += S.rhs_a[t];
+                s1b += S.rhs_b[t];
+                sv += S.nval[t];
+            }
+            s1a = warp_sum(s1a);
+            s1b = warp_sum(s1b);
+            sv = warp_sum(sv);
+            s1a = __shfl_sync(0xffffffffu, s1a, 0);
+            s1b = __shfl_sync(0xffffffffu, s1b, 0);
+            sv = __shfl_sync(0xffffffffu, sv, 0);
+            const double mu = (s1a - 1.0) / s1b;
+            for (int t = lane; t < n; t += 32) S.rhs_a[t] = S.rhs_a[t] - mu * S.rhs_b[t];      // kriging weights
+            if (lane == 0) S.scratch[36] = sv / (double)n;                                     // local mean of the neighbours
+        }
+        __syncthreads();
+        {
+            // sum w_i rho_i and sum w_i (v_i - mean) over the first n threads (rho_keep lives in their registers)
+            const double mean = S.scratch[36];
+            double pv = 0.0, pe = 0.0;
+            if (tid < n) {
+                const double w = S.rhs_a[tid];
+                pv = w * rho_keep;
+                pe = w * (S.nval[tid] - mean);
+            }
+            const double sum_v = block_sum<SGS_THREADS>(pv, S.scratch);
+            const double sum_e = block_sum<SGS_THREADS>(pe, S.scratch);
+            if (tid == 0) {
+                const double var = fabs(s.sill - sum_v);
+                const double est = mean + sum_e;
+                double zn;
+                if (INJECT) zn = zn_in[k];
+                else {
+                    double z1;
+                    box_muller(rng((uint32_t)node, it_lo, it_hi, 6u), zn, z1);       // stream 6: node normals
+                }
+                S.blk_z[node] = est + sqrt(var) * zn;                                  // MCMC.py:168
+            }
+        }
+        __syncthreads();
+    }
+
+    // (3) candidate bed of the block = inverse normal score of the simulated values            MCMC.py:1776-1777
+    for (int e = tid; e < nblk; e += SGS_THREADS) S.cand[e] = nst_inverse(s, S.blk_z[e]);
+    __syncthreads();
+    auto full_bed = [&](int i, int j) -> double {
+        const int64_t idx = (int64_t)i * W + j;
+        const double bc = (i >= x0 && i < x1 && j >= y0 && j < y1) ? S.cand[(i - x0) * bw + (j - y0)] : __ldcg(bedc + idx);
+        return s.trend ? add_rn(bc, __ldg(s.trend + idx)) : bc;
+    };
+    // residual on the block plus its one-cell ring (everything a changed bed cell can influence)
+    const int rx0 = max(x0 - 1, 0), rx1 = min(x1 + 1, H), ry0 = max(y0 - 1, 0), ry1 = min(y1 + 1, W);
+    const int rh = rx1 - rx0, rw = ry1 - ry0;
+    double delta = 0.0;
+    int dviol = 0;
+    for (int e = tid; e < rh * rw; e += SGS_THREADS) {
+        const int ri = e / rw, rj = e - ri * rw;
+        const int i = rx0 + ri, j = ry0 + rj;
+        const int64_t idx = (int64_t)i * W + j;
+        const int jl = max(j - 1, 0), jr = min(j + 1, W - 1), iu = max(i - 1, 0), id = min(i + 1, H - 1);
+        const bool ex = (j == 0) || (j == W - 1), ey = (i == 0) || (i == H - 1);
+        const double2 xr = __ldg(d.sv + (int64_t)i * W + jr), xl = __ldg(d.sv + (int64_t)i * W + jl);
+        const double2 yd = __ldg(d.sy + (int64_t)id * W + j), yu = __ldg(d.sy + (int64_t)iu * W + j);
+        const double2 hs = __ldg(d.ds + idx);
+        const double fr = mul_rn(xr.y, sub_rn(xr.x, full_bed(i, jr))), fl = mul_rn(xl.y, sub_rn(xl.x, full_bed(i, jl)));
+        const double fd = mul_rn(yd.y, sub_rn(yd.x, full_bed(id, j))), fu = mul_rn(yu.y, sub_rn(yu.x, full_bed(iu, j)));
+        const double dx = div_const(sub_rn(fr, fl), ex ? d.res : d.two_res, ex ? d.r_res : d.r_two_res);
+        const double dy = div_const(sub_rn(fd, fu), ey ? d.res : d.two_res, ey ? d.r_res : d.r_two_res);
+        const double rnew = sub_rn(add_rn(add_rn(dx, dy), hs.x), hs.y);
+        S.newres[e] = rnew;
+        if (__ldg(d.flags + idx) & FLAG_MC) {
+            const double rold = __ldcg(mcres + idx);
+            delta += ((rnew == rnew) ? rnew * rnew : 0.0) - ((rold == rold) ? rold * rold : 0.0);
+        }
+        if (i >= x0 && i < x1 && j >= y0 && j < y1 && __ldg(s.grounded + idx) == 1) {       // guard delta on the block
+            const double sf = __ldg(d.surf + idx);
+            const double oldfull = s.trend ? add_rn(__ldcg(bedc + idx), __ldg(s.trend + idx)) : __ldcg(bedc + idx);
+            dviol += (sub_rn(sf, full_bed(i, j)) <= 0.0) - (sub_rn(sf, oldfull) <= 0.0);
+        }
+    }
+    const double dsum = block_sum<SGS_THREADS>(delta, S.scratch);
+    const double dv = block_sum<SGS_THREADS>((double)dviol, S.scratch);
+    if (tid == 0) {
+        const int nviol_next = nviol + (int)dv;
+        const double ssq_next = ssq + dsum;
+        const double loss_prev = div_rn(ssq, d.two_sigma2);
+        double loss_next = div_rn(ssq_next, d.two_sigma2);
+        if (nviol_next > 0) loss_next = __longlong_as_double(0x7ff0000000000000LL);        // MCMC.py:1794-1795
+        double acc;
+        if (loss_prev > loss_next) acc = 1.0;
+        else {
+            const double ex = exp(loss_prev - loss_next);
+            acc = (ex < 1.0) ? ex : 1.0;
+        }
+        S.accept = (S.u <= acc) ? 1 : 0;
+        S.scratch[34] = ssq_next;
+        S.scratch[35] = loss_next;
+        S.scratch[37] = (double)nviol_next;
+    }
+    __syncthreads();
+    if (loss_next_out && tid == 0) *loss_next_out = S.scratch[35];
+    if (S.accept) {
+        ssq = S.scratch[34];
+        nviol = (int)S.scratch[37];
+        for (int e = tid; e < nblk; e += SGS_THREADS) {
+            const int bi = e / bw, bj = e - bi * bw;
+            const int64_t idx = (int64_t)(x0 + bi) * W + (y0 + bj);
+            const double c = S.cand[e];
+            __stcg(bedc + idx, c);
+            __stcg(z + idx, nst_forward(s, c));          // the reference re-transforms the accepted bed every step (MCMC.py:1767)
+            if (resampled) resampled[idx] += 1;          // MCMC.py:1806
+        }
+        for (int e = tid; e < rh * rw; e += SGS_THREADS) {
+            const int ri = e / rw, rj = e - ri * rw;
+            __stcg(mcres + (int64_t)(rx0 + ri) * W + (ry0 + rj), S.newres[e]);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void sgs_window(SgsShared& S, int H, int W) {
+    // MCMC.py:1759-1762: int(index - size/2) truncates toward zero, then clamps
+    S.x0 = max(0, (int)((double)S.ix - (double)S.bsx / 2.0));
+    S.x1 = min(H, (int)((double)S.ix + (double)S.bsx / 2.0));
+    S.y0 = max(0, (int)((double)S.iy - (double)S.bsy / 2.0));
+    S.y1 = min(W, (int)((double)S.iy + (double)S.bsy / 2.0));
+}
+
+__global__ void __launch_bounds__(SGS_THREADS)
+    sgs_step_injected_kernel(GmcDev d, SgsDev s, double* bedc_all, double* z_all, double* mcres_all, double* ssq_all,
+                             int32_t* nviol_all, const int32_t* __restrict__ centre, const int32_t* __restrict__ bs,
+                             const int32_t* __restrict__ path, const double* __restrict__ zn, int64_t path_stride,
+                             const double* __restrict__ u, uint8_t* accepted_out, double* loss_out, double* loss_next_out,
+                             int32_t* resampled_all, int32_t* err_out) {
+    extern __shared__ __align__(16) unsigned char sgs_raw[];
+    SgsShared& S = *reinterpret_cast<SgsShared*>(sgs_raw);
+    const int c = blockIdx.x;
+    const int64_t plane = (int64_t)d.H * d.W;
+    if (threadIdx.x == 0) {
+        S.ix = centre[2 * c];
+        S.iy = centre[2 * c + 1];
+        S.bsx = bs[2 * c];
+        S.bsy = bs[2 * c + 1];
+        S.u = u[c];
+        S.err = 0;
+        sgs_window(S, d.H, d.W);
+    }
+    __syncthreads();
+    double ssq = ssq_all[c];
+    int nviol = nviol_all[c];
+    const Philox rng(0ull);
+    sgs_one_step<true>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, path + c * path_stride,
+                       zn + c * path_stride, rng, 0u, 0u, resampled_all ? resampled_all + c * plane : nullptr,
+                       loss_next_out ? loss_next_out + c : nullptr);
+    if (threadIdx.x == 0) {
+        ssq_all[c] = ssq;
+        nviol_all[c] = nviol;
+        if (accepted_out) accepted_out[c] = (uint8_t)S.accept;
+        if (loss_out) loss_out[c] = div_rn(ssq, d.two_sigma2);
+        if (err_out && S.err) atomicOr(err_out, 1);
+    }
+}
+
+__global__ void __launch_bounds__(SGS_THREADS)
+    sgs_run_kernel(GmcDev d, SgsDev s, double* bedc_all, double* z_all, double* mcres_all, double* ssq_all, int32_t* nviol_all,
+                   const uint64_t* __restrict__ seeds, uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache,
+                   int32_t* blocks_cache, int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int32_t* err_out) {
+    extern __shared__ __align__(16) unsigned char sgs_raw[];
+    SgsShared& S = *reinterpret_cast<SgsShared*>(sgs_raw);
+    const int c = blockIdx.x;
+    const int64_t plane = (int64_t)d.H * d.W;
+    const Philox rng(seeds[c]);
+    double ssq = ssq_all[c];
+    int nviol = nviol_all[c];
+    if (threadIdx.x == 0) S.err = 0;
+    for (int k = 0; k < n_steps; ++k) {
+        const uint64_t it = iter0 + (uint64_t)k;
+        const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
+        if (threadIdx.x == 0) {
+            // chain stream: centre (uniform over region cells), block sizes (upper bound exclusive), acceptance uniform
+            const uint4 c0 = rng(0u, it_lo, it_hi, GMC_STREAM_CHAIN);
+            const uint4 c1 = rng(1u, it_lo, it_hi, GMC_STREAM_CHAIN);
+            const uint4 c2 = rng(2u, it_lo, it_hi, GMC_STREAM_CHAIN);
+            if (d.n_centre_cells > 0) {
+                const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
+                S.ix = cell / d.W;
+                S.iy = cell - S.ix * d.W;
+            } else {
+                S.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
+                S.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
+            }
+            S.u = u01_halfopen(c1.x, c1.y);
+            S.bsx = s.bmin_x + (int)bounded_u64(c2.x, c2.y, (uint64_t)(s.bmax_x - s.bmin_x));
+            S.bsy = s.bmin_y + (int)bounded_u64(c2.z, c2.w, (uint64_t)(s.bmax_y - s.bmin_y));
+            sgs_window(S, d.H, d.W);
+        }
+        __syncthreads();
+        sgs_one_step<false>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, nullptr, nullptr,
+                            rng, it_lo, it_hi, resampled_all ? resampled_all + c * plane : nullptr, nullptr);
+        if (threadIdx.x == 0) {
+            const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
+            if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
+            if (step_cache) step_cache[slot] = (uint8_t)S.accept;
+            if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(S.ix, S.iy, S.bsx, S.bsy);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        ssq_all[c] = ssq;
+        nviol_all[c] = nviol;
+        if (err_out && S.err) atomicOr(err_out, 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host entry points
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+static int upload(const T* src, size_t n, T** dst, void** slot) {
+    GMC_CUDA(cudaMalloc(dst, n * sizeof(T)));
+    GMC_CUDA(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyDefault));
+    *slot = *dst;
+    return GMC_OK;
+}
+
+static void sgs_free(gmc_sgs_state* st) {
+    if (!st) return;
+    for (void*& p : st->owned) {
+        cudaFree(p);
+        p = nullptr;
+    }
+}
+
+extern "C" int gmc_sgs_setup(gmc_ctx* c, const double* trend, const double* zcond, const uint8_t* grounded,
+                             const double* quantiles, const double* references, int n_quantiles, const int16_t* oct_off,
+                             const int32_t* oct_cnt, int lmax, int hw, int num_points, const double* lut, double sill,
+                             int block_min_x, int block_max_x, int block_min_y, int block_max_y) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: ctx is NULL");
+    if (!c->have_static) GMC_FAIL(GMC_ESTATE, "gmc_sgs_setup: call gmc_set_static first");
+    if (!zcond || !grounded || !oct_off || !oct_cnt || !lut) GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: NULL argument");
+    if ((quantiles == nullptr) != (references == nullptr) || (quantiles && n_quantiles < 2))
+        GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: quantiles/references must both be given (>= 2 entries) or both be NULL");
+    if (num_points < 8 || num_points > SGS_MAX_NEIGH)
+        GMC_FAIL(GMC_EUNSUPPORTED, "gmc_sgs_setup: num_points=%d outside [8,%d] (the reference takes num_points//8 per octant)", num_points, SGS_MAX_NEIGH);
+    if (hw < 1 || lmax < 1) GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: empty search stencil");
+    if (block_min_x < 1 || block_min_y < 1 || block_max_x <= block_min_x || block_max_y <= block_min_y)
+        GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: block sizes are drawn from [min, max) and need max > min >= 1 (MCMC.py:1755-1756)");
+    if (block_max_x - 1 > SGS_MAX_BLOCK || block_max_y - 1 > SGS_MAX_BLOCK)
+        GMC_FAIL(GMC_EUNSUPPORTED, "gmc_sgs_setup: blocks larger than %d cells per edge are not supported", SGS_MAX_BLOCK);
+    GMC_CUDA(cudaSetDevice(c->device));
+    if (!c->sgs) {
+        c->sgs = new gmc_sgs_state();
+        memset(c->sgs, 0, sizeof(gmc_sgs_state));
+    }
+    gmc_sgs_state* st = c->sgs;
+    sgs_free(st);
+    st->ready = false;
+    const size_t n = (size_t)c->H * c->W;
+    SgsDev& s = st->dev;
+    memset(&s, 0, sizeof(s));
+    double* dp = nullptr;
+    uint8_t* up = nullptr;
+    int16_t* sp = nullptr;
+    int32_t* ip = nullptr;
+    int rc;
+    if (trend) {
+        if ((rc = upload(trend, n, &dp, &st->owned[0]))) return rc;
+        s.trend = dp;
+    }
+    if ((rc = upload(zcond, n, &dp, &st->owned[1]))) return rc;
+    s.zcond = dp;
+    if ((rc = upload(grounded, n, &up, &st->owned[2]))) return rc;
+    s.grounded = up;
+    if (quantiles) {
+        if ((rc = upload(quantiles, (size_t)n_quantiles, &dp, &st->owned[3]))) return rc;
+        s.quant = dp;
+        if ((rc = upload(references, (size_t)n_quantiles, &dp, &st->owned[4]))) return rc;
+        s.refs = dp;
+        s.nq = n_quantiles;
+    }
+    if ((rc = upload(oct_off, (size_t)8 * lmax * 2, &sp, &st->owned[5]))) return rc;
+    s.oct_off = sp;
+    if ((rc = upload(oct_cnt, (size_t)8, &ip, &st->owned[6]))) return rc;
+    s.oct_cnt = ip;
+    s.lut_w = 4 * hw + 1;
+    if ((rc = upload(lut, (size_t)s.lut_w * s.lut_w, &dp, &st->owned[7]))) return rc;
+    s.lut = dp;
+    s.lmax = lmax;
+    s.hw = hw;
+    s.per_oct = num_points / 8;
+    s.sill = sill;
+    s.bmin_x = block_min_x;
+    s.bmax_x = block_max_x;
+    s.bmin_y = block_min_y;
+    s.bmax_y = block_max_y;
+    GMC_CUDA(cudaFuncSetAttribute(sgs_step_injected_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
+    GMC_CUDA(cudaFuncSetAttribute(sgs_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
+    st->ready = true;
+    return GMC_OK;
+}
+
+void gmc_sgs_destroy(gmc_ctx* c) {
+    if (c && c->sgs) {
+        sgs_free(c->sgs);
+        delete c->sgs;
+        c->sgs = nullptr;
+    }
+}
+
+static int sgs_check(gmc_ctx* c, int C, const char* who) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "%s: ctx is NULL", who);
+    if (!c->sgs || !c->sgs->ready) GMC_FAIL(GMC_ESTATE, "%s: call gmc_sgs_setup first", who);
+    if (C < 1 || C > c->max_chains) GMC_FAIL(GMC_ESHAPE, "%s: C=%d outside [1,%d]", who, C, c->max_chains);
+    GMC_CUDA(cudaSetDevice(c->device));
+    return GMC_OK;
+}
+
+extern "C" int gmc_sgs_transform(gmc_ctx* c, const double* in, double* out, int64_t n, int inverse, void* stream) {
+    int rc = sgs_check(c, 1, "gmc_sgs_transform");
+    if (rc) return rc;
+    if (!in || !out || n < 1) GMC_FAIL(GMC_EINVAL, "gmc_sgs_transform: bad argument");
+    sgs_transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(c->sgs->dev, in, out, n, inverse);
+    c->launches++;
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+extern "C" int gmc_sgs_init(gmc_ctx* c, const double* bed, double* bedc, double* z, double* mcres, double* ssq, int32_t* nviol,
+                            double* scratch_full, int C, void* stream) {
+    int rc = sgs_check(c, C, "gmc_sgs_init");
+    if (rc) return rc;
+    if (!bed || !bedc || !z || !mcres || !ssq || !nviol || !scratch_full) GMC_FAIL(GMC_EINVAL, "gmc_sgs_init: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)C * c->H * c->W;
+    GMC_CUDA(cudaMemsetAsync(nviol, 0, (size_t)C * sizeof(int32_t), st));
+    sgs_init_kernel<<<dim3(64, C), 256, 0, st>>>(c->dev, c->sgs->dev, bed, bedc, z, nviol, C);
+    sgs_fullbed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->dev, c->sgs->dev, bedc, scratch_full, n);
+    c->launches += 2;
+    GMC_CUDA(cudaGetLastError());
+    // residual + loss of the (re-assembled) full bed, like MCMC.py:1663-1669
+    return gmc_residual_loss(c, scratch_full, mcres, nullptr, ssq, C, stream);
+}
+
+extern "C" int gmc_sgs_step_injected(gmc_ctx* c, double* bedc, double* z, double* mcres, double* ssq, int32_t* nviol,
+                                     const int32_t* centre, const int32_t* block_size, const int32_t* path, const double* znorm,
+                                     int64_t path_stride, const double* u, uint8_t* accepted_out, double* loss_out,
+                                     double* loss_next_out, int32_t* resampled, int32_t* err_flag, int C, void* stream) {
+    int rc = sgs_check(c, C, "gmc_sgs_step_injected");
+    if (rc) return rc;
+    if (!bedc || !z || !mcres || !ssq || !nviol || !centre || !block_size || !path || !znorm || !u)
+        GMC_FAIL(GMC_EINVAL, "gmc_sgs_step_injected: NULL argument");
+    sgs_step_injected_kernel<<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
+        c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, centre, block_size, path, znorm, path_stride, u, accepted_out, loss_out,
+        loss_next_out, resampled, err_flag);
+    c->launches++;
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, double* ssq, int32_t* nviol, const uint64_t* seeds,
+                           uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache,
+                           int64_t cache_stride, int64_t cache_offset, int32_t* resampled, int32_t* err_flag, int C, void* stream) {
+    int rc = sgs_check(c, C, "gmc_sgs_run");
+    if (rc) return rc;
+    if (!bedc || !z || !mcres || !ssq || !nviol || !seeds) GMC_FAIL(GMC_EINVAL, "gmc_sgs_run: NULL argument");
+    if (n_steps < 0) GMC_FAIL(GMC_EINVAL, "gmc_sgs_run: negative n_steps");
+    if ((loss_cache || step_cache || blocks_cache) && (cache_offset < 0 || cache_offset + n_steps > cache_stride))
+        GMC_FAIL(GMC_ESHAPE, "gmc_sgs_run: cache window exceeds stride");
+    if (n_steps == 0) return GMC_OK;
+    sgs_run_kernel<<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds,
+                                                                              iter0, n_steps, loss_cache, step_cache, blocks_cache,
+                                                                              cache_stride, cache_offset, resampled, err_flag);
+    c->launches++;
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}

@@ -28,3 +28,23 @@ def oracle_sgs_setup(case):
                     nst=nst, vario=sgs_vario_dict(case["vario"]), num_points=case["neighbors"], radius=case["radius"],
                     block=tuple(case["blocks"]))
     return g, su
+
+
+def product_sgs_chain(case, g=None):
+    """mcmc_gpu_b200's chain_sgs configured like the reference tutorial (T4_SmallScaleChain.ipynb cells 20-38)."""
+    from gpu_helpers import quiet
+    from mcmc_gpu_b200 import MCMC
+    g = build_sgs_inputs(case) if g is None else g
+    ch = quiet(MCMC.chain_sgs, g["xx"], g["yy"], g["bed_init"], g["surf"], g["velx"], g["vely"], g["dhdt"], g["smb"], g["cond_bed"],
+               g["data_mask"], g["grounded_ice_mask"], g["resolution"])
+    quiet(ch.set_update_region, True, g["highvel_mask"])
+    ch.set_loss_type(sigma_mc=case["sigma_mc"], massConvInRegion=True)
+    ch.set_block_sizes(*case["blocks"])
+    ch.set_normal_transformation(g.get("nst"), do_transform=case["transform"])
+    ch.set_trend(g["trend"], detrend_map=case["detrend"])
+    v = case["vario"]
+    quiet(ch.set_variogram, v["vtype"], v["range"], v["sill"], v["nugget"], isotropic=v["isotropic"],
+          vario_smoothness=v["smoothness"], vario_azimuth=v["azimuth"])
+    quiet(ch.set_sgs_param, case["neighbors"], case["radius"])
+    ch.set_random_generator(case["seed"])
+    return ch, g

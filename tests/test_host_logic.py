@@ -76,3 +76,50 @@ def test_philox_keys_are_distinct_and_stable():
     keys = {philox_key(s, s) for s in range(4096)}
     assert len(keys) == 4096
     assert philox_key(5, 5) == philox_key(5) and philox_key(5, 6) != philox_key(5, 5)
+
+
+def test_sgs_octant_stencil_reproduces_the_reference_search():
+    """The host-built, pre-sorted octant offset lists select exactly the neighbours of neighbors.py:4-64 (stable ties)."""
+    from mcmc_gpu_b200 import sgs_tables as T
+    from oracle import sgs_oracle as S
+    off, cnt, hw = T.octant_stencil(500.0, 500.0, 4e3)
+    H = W = 41
+    xx, yy = np.meshgrid(np.arange(W) * 500.0, np.arange(H) * 500.0)
+    rng = np.random.default_rng(0)
+    grid = rng.standard_normal((H, W))
+    cond = rng.random((H, W)) < 0.7
+    grid[~cond] = np.nan
+    for (i, j) in [(20, 20), (0, 5), (40, 40), (3, 38), (17, 0)]:
+        cond[i, j] = False
+        grid[i, j] = np.nan
+        nb = S.octant_neighbors(i, j, xx, yy, grid, cond, 4e3, 24, hw)
+        mine = []
+        for o in range(8):
+            k = 0
+            for t in range(cnt[o]):
+                ci, cj = i + off[o, t, 0], j + off[o, t, 1]
+                if 0 <= ci < H and 0 <= cj < W and cond[ci, cj]:
+                    mine.append((ci, cj))
+                    k += 1
+                    if k == 3:
+                        break
+        assert np.array_equal(np.array(mine), nb[:, 3:5].astype(int)), (i, j)
+
+
+def test_sgs_covariance_lut_matches_the_kriging_matrices():
+    from scipy.spatial.distance import pdist, squareform
+    from mcmc_gpu_b200 import sgs_tables as T
+    from oracle import sgs_oracle as S
+    for vario in (dict(azimuth=30.0, nugget=0.0, major_range=4000.0, minor_range=2500.0, sill=900.0, vtype="Exponential"),
+                  dict(azimuth=0, nugget=0.1, major_range=3000.0, minor_range=3000.0, sill=1.0, vtype="Matern", s=1.2259),
+                  dict(azimuth=75.0, nugget=0.0, major_range=2000.0, minor_range=900.0, sill=2.0, vtype="Spherical"),
+                  dict(azimuth=0, nugget=0.0, major_range=1500.0, minor_range=1500.0, sill=1.0, vtype="Gaussian")):
+        hw = 6
+        lut = T.covariance_lut(500.0, 250.0, hw, vario)
+        rng = np.random.default_rng(1)
+        pts = rng.integers(-hw, hw + 1, size=(12, 2))                        # (di, dj) offsets of neighbours
+        xy = np.stack([pts[:, 1] * 500.0, pts[:, 0] * 250.0], axis=1)
+        R = S.rotation_matrix(vario["azimuth"], vario["major_range"], vario["minor_range"])
+        Sigma = S.covariance(vario["vtype"], squareform(pdist(xy @ R)), vario["sill"], vario["nugget"], vario.get("s"))
+        mine = np.array([[lut[a[0] - b[0] + 2 * hw, a[1] - b[1] + 2 * hw] for b in pts] for a in pts])
+        assert np.allclose(mine, Sigma, rtol=1e-12, atol=1e-13), vario["vtype"]
