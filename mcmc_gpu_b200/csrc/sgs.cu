@@ -21,7 +21,8 @@
 #define SGS_THREADS 256
 #define SGS_MAX_BLOCK 32          // largest block edge (cells)
 #define SGS_MAX_NEIGH 64          // largest num_points
-#define SGS_SIG_PITCH (SGS_MAX_NEIGH + 1)
+#define SGS_SIG_PITCH (SGS_MAX_NEIGH + 3)   // augmented matrix [Sigma | rho | 1], odd pitch
+#define SGS_NEAR 64               // offsets per octant staged in shared memory
 
 struct SgsDev {
     const double* trend;          // [H][W] or nullptr
@@ -37,6 +38,7 @@ struct SgsDev {
     int lut_w;                    // 4hw+1
     double sill;
     int bmin_x, bmax_x, bmin_y, bmax_y;
+    long long* phase;             // optional cycle counters (debug), see gmc_debug_phase_timing
 };
 
 struct gmc_sgs_state {
@@ -125,7 +127,7 @@ struct SgsShared {
     int16_t ndi[SGS_MAX_NEIGH], ndj[SGS_MAX_NEIGH];
     int oct_n[8];
     int path[SGS_MAX_BLOCK * SGS_MAX_BLOCK];
-    unsigned long long keys[SGS_MAX_BLOCK * SGS_MAX_BLOCK];
+    short2 near_off[8][SGS_NEAR];                      // the nearest offsets of every octant (almost every search ends here)
     double scratch[40];
     int ix, iy, bsx, bsy, x0, x1, y0, y1, accept, n_nb, err;
     double u;
@@ -142,6 +144,14 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
     const int H = d.H, W = d.W, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int x0 = S.x0, x1 = S.x1, y0 = S.y0, y1 = S.y1;
     const int bh = x1 - x0, bw = y1 - y0, nblk = bh * bw;
+    long long tclk = (s.phase && tid == 0) ? clock64() : 0;
+    auto mark = [&](int ph) {
+        if (s.phase && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(reinterpret_cast<unsigned long long*>(s.phase + ph), (unsigned long long)(now - tclk));
+            tclk = now;
+        }
+    };
     // (1) block <- normal-scored conditioning data (NaN where there is none)              MCMC.py:1771
     for (int e = tid; e < nblk; e += SGS_THREADS) {
         const int bi = e / bw, bj = e - bi * bw;
@@ -151,6 +161,7 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
     if (INJECT) {
         for (int e = tid; e < nblk; e += SGS_THREADS) S.path[e] = path_in[e];
     } else {
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(S.sig);      // the kriging matrix is idle here
         int npad = 1;
         while (npad < nblk) npad <<= 1;
         for (int e = tid; e < npad; e += SGS_THREADS) {
@@ -159,7 +170,7 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
                 const uint4 r = rng((uint32_t)e, it_lo, it_hi, 5u);          // stream 5: path keys
                 k = ((((unsigned long long)r.x << 32) | r.y) & ~0x3ffull) | (unsigned long long)e;   // unique: index in low bits
             }
-            S.keys[e] = k;
+            keys[e] = k;
         }
         __syncthreads();
         for (int k2 = 2; k2 <= npad; k2 <<= 1)                                 // bitonic sort, ascending
@@ -167,17 +178,19 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
                 for (int e = tid; e < npad; e += SGS_THREADS) {
                     const int p = e ^ j2;
                     if (p > e) {
-                        const unsigned long long a = S.keys[e], b = S.keys[p];
+                        const unsigned long long a = keys[e], b = keys[p];
                         const bool up = (e & k2) == 0;
-                        if ((a > b) == up) { S.keys[e] = b; S.keys[p] = a; }
+                        if ((a > b) == up) { keys[e] = b; keys[p] = a; }
                     }
                 }
                 __syncthreads();
             }
-        for (int e = tid; e < nblk; e += SGS_THREADS) S.path[e] = (int)(S.keys[e] & 0x3ffull);
+        for (int e = tid; e < nblk; e += SGS_THREADS) S.path[e] = (int)(keys[e] & 0x3ffull);
+        __syncthreads();
     }
     __syncthreads();
 
+    mark(0);
     // (2) sequential simulation along the path                                              MCMC.py:130-169
     for (int k = 0; k < nblk; ++k) {
         const int node = S.path[k];
@@ -196,8 +209,14 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
                 int di = 0, dj = 0;
                 double v = 0.0;
                 if (t < cnt) {
-                    di = off[2 * t];
-                    dj = off[2 * t + 1];
+                    if (t < SGS_NEAR) {
+                        const short2 o2 = S.near_off[wid][t];
+                        di = o2.x;
+                        dj = o2.y;
+                    } else {
+                        di = off[2 * t];
+                        dj = off[2 * t + 1];
+                    }
                     const int ci = i + di, cj = j + dj;
                     if (ci >= 0 && ci < H && cj >= 0 && cj < W) {
                         if (ci >= x0 && ci < x1 && cj >= y0 && cj < y1) v = S.blk_z[(ci - x0) * bw + (cj - y0)];
@@ -218,6 +237,7 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
             if (lane == 0) S.oct_n[wid] = min(found, s.per_oct);
         }
         __syncthreads();
+        mark(1);
         // (b) compact the octant lists (octant order -4..3, each sorted by distance) -> n neighbours
         int n = 0, start[8];
 #pragma unroll
@@ -250,10 +270,21 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
             S.nval[dst] = mval;
         }
         __syncthreads();
+        mark(2);
         // (c) assemble Sigma (n x n), rho and the ones vector                                   _krige.py:20-33
-        for (int t = tid; t < n * n; t += SGS_THREADS) {
-            const int a = t / n, b = t - a * n;
-            S.sig[a * SGS_SIG_PITCH + b] = lut_cov(s, S.ndi[a] - S.ndi[b], S.ndj[a] - S.ndj[b]);
+        for (int t0 = tid; t0 < n * n; t0 += 4 * SGS_THREADS) {          // 4 independent table loads in flight per thread
+            double cv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + q * SGS_THREADS;
+                const int a = (t < n * n) ? t / n : 0, b = (t < n * n) ? t - a * n : 0;
+                cv[q] = lut_cov(s, S.ndi[a] - S.ndi[b], S.ndj[a] - S.ndj[b]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int t = t0 + q * SGS_THREADS;
+                if (t < n * n) S.sig[(t / n) * SGS_SIG_PITCH + (t % n)] = cv[q];
+            }
         }
         if (tid < n) {
             S.rhs_a[tid] = lut_cov(s, -S.ndi[tid], -S.ndj[tid]);
@@ -262,41 +293,55 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
         __syncthreads();
         // rho is needed again for the variance: keep a register copy in the first n threads
         const double rho_keep = (tid < n) ? S.rhs_a[tid] : 0.0;
-        // (d) elimination without pivoting (SPD block), both right-hand sides carried along
-        for (int p = 0; p < n - 1; ++p) {
-            const double inv = 1.0 / S.sig[p * SGS_SIG_PITCH + p];
-            const int m = n - 1 - p;                    // rows below the pivot
-            for (int t = tid; t < m * (m + 2); t += SGS_THREADS) {
-                const int r = p + 1 + t / (m + 2), cidx = t % (m + 2);
-                const double f = S.sig[r * SGS_SIG_PITCH + p] * inv;
-                if (cidx < m) {
-                    const int cc = p + 1 + cidx;
-                    S.sig[r * SGS_SIG_PITCH + cc] -= f * S.sig[p * SGS_SIG_PITCH + cc];
-                } else if (cidx == m) S.rhs_a[r] -= f * S.rhs_a[p];
-                else S.rhs_b[r] -= f * S.rhs_b[p];
+        mark(3);
+        // (d) Gauss-Jordan elimination without pivoting (SPD block) on the augmented matrix [Sigma | rho | 1]: column p
+        // is cleared from every other row, so the system ends diagonal and no serial back substitution is needed.
+        // A warp owns rows wid, wid+8, ...; its lanes sweep the live columns p+1 .. n+1 (conflict-free, no index math).
+        if (tid < n) {
+            S.sig[tid * SGS_SIG_PITCH + n] = S.rhs_a[tid];
+            S.sig[tid * SGS_SIG_PITCH + n + 1] = S.rhs_b[tid];
+        }
+        __syncthreads();
+        for (int p = 0; p < n; ++p) {
+            const double* prow = S.sig + p * SGS_SIG_PITCH;
+            const double inv = 1.0 / prow[p];
+            // the pivot row's live entries sit in registers (<= 3 per lane for n + 2 <= 66 columns); all loads of a row
+            // group are issued before the stores so the shared-memory round trips overlap instead of serialising
+            const int c0 = p + 1 + lane, c1 = c0 + 32, c2 = c0 + 64;
+            const double p0 = (c0 < n + 2) ? prow[c0] : 0.0, p1 = (c1 < n + 2) ? prow[c1] : 0.0, p2 = (c2 < n + 2) ? prow[c2] : 0.0;
+            constexpr int RG = 4;                                   // rows per group
+            for (int r0 = wid; r0 < n; r0 += RG * (SGS_THREADS / 32)) {
+                double f[RG], a0[RG], a1[RG], a2[RG];
+#pragma unroll
+                for (int q = 0; q < RG; ++q) {
+                    const int r = r0 + q * (SGS_THREADS / 32);
+                    const bool on = (r < n) && (r != p);
+                    const double* row = S.sig + (on ? r : p) * SGS_SIG_PITCH;
+                    f[q] = on ? row[p] * inv : 0.0;
+                    a0[q] = (c0 < n + 2) ? row[c0] : 0.0;
+                    a1[q] = (c1 < n + 2) ? row[c1] : 0.0;
+                    a2[q] = (c2 < n + 2) ? row[c2] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < RG; ++q) {
+                    const int r = r0 + q * (SGS_THREADS / 32);
+                    if ((r < n) && (r != p)) {
+                        double* row = S.sig + r * SGS_SIG_PITCH;
+                        if (c0 < n + 2) row[c0] = a0[q] - f[q] * p0;
+                        if (c1 < n + 2) row[c1] = a1[q] - f[q] * p1;
+                        if (c2 < n + 2) row[c2] = a2[q] - f[q] * p2;
+                    }
+                }
             }
             __syncthreads();
         }
-        // back substitution by warp 0 (upper triangle), two right-hand sides
-        if (wid == 0) {
-            for (int r = n - 1; r >= 0; --r) {
-                double sa = 0.0, sb = 0.0;
-                for (int cc = r + 1 + lane; cc < n; cc += 32) {
-                    const double a = S.sig[r * SGS_SIG_PITCH + cc];
-                    sa += a * S.rhs_a[cc];
-                    sb += a * S.rhs_b[cc];
-                }
-                sa = warp_sum(sa);
-                sb = warp_sum(sb);
-                if (lane == 0) {
-                    const double dg = S.sig[r * SGS_SIG_PITCH + r];
-                    S.rhs_a[r] = (S.rhs_a[r] - sa) / dg;
-                    S.rhs_b[r] = (S.rhs_b[r] - sb) / dg;
-                }
-                __syncwarp();
-            }
+        if (tid < n) {
+            const double dg = S.sig[tid * SGS_SIG_PITCH + tid];
+            S.rhs_a[tid] = S.sig[tid * SGS_SIG_PITCH + n] / dg;
+            S.rhs_b[tid] = S.sig[tid * SGS_SIG_PITCH + n + 1] / dg;
         }
         __syncthreads();
+        mark(4);
         // (e) Lagrange multiplier, weights, estimate and variance (warp 0)                        _krige.py:36-43
         if (wid == 0) {
             double s1a = 0.0, s1b = 0.0, sv = 0.0;
@@ -342,6 +387,7 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
         __syncthreads();
     }
 
+    mark(5);
     // (3) candidate bed of the block = inverse normal score of the simulated values            MCMC.py:1776-1777
     for (int e = tid; e < nblk; e += SGS_THREADS) S.cand[e] = nst_inverse(s, S.blk_z[e]);
     __syncthreads();
@@ -418,6 +464,16 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
         }
     }
     __syncthreads();
+    mark(6);
+}
+
+__device__ __forceinline__ void sgs_stage_offsets(const SgsDev& s, SgsShared& S) {
+    for (int t = threadIdx.x; t < 8 * SGS_NEAR; t += SGS_THREADS) {
+        const int o = t / SGS_NEAR, k = t - o * SGS_NEAR;
+        short2 v = make_short2(0, 0);
+        if (k < s.lmax) v = make_short2(s.oct_off[((int64_t)o * s.lmax + k) * 2], s.oct_off[((int64_t)o * s.lmax + k) * 2 + 1]);
+        S.near_off[o][k] = v;
+    }
 }
 
 __device__ __forceinline__ void sgs_window(SgsShared& S, int H, int W) {
@@ -438,6 +494,7 @@ __global__ void __launch_bounds__(SGS_THREADS)
     SgsShared& S = *reinterpret_cast<SgsShared*>(sgs_raw);
     const int c = blockIdx.x;
     const int64_t plane = (int64_t)d.H * d.W;
+    sgs_stage_offsets(s, S);
     if (threadIdx.x == 0) {
         S.ix = centre[2 * c];
         S.iy = centre[2 * c + 1];
@@ -475,6 +532,7 @@ __global__ void __launch_bounds__(SGS_THREADS)
     double ssq = ssq_all[c];
     int nviol = nviol_all[c];
     if (threadIdx.x == 0) S.err = 0;
+    sgs_stage_offsets(s, S);
     for (int k = 0; k < n_steps; ++k) {
         const uint64_t it = iter0 + (uint64_t)k;
         const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
@@ -669,6 +727,7 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
     if ((loss_cache || step_cache || blocks_cache) && (cache_offset < 0 || cache_offset + n_steps > cache_stride))
         GMC_FAIL(GMC_ESHAPE, "gmc_sgs_run: cache window exceeds stride");
     if (n_steps == 0) return GMC_OK;
+    c->sgs->dev.phase = c->d_phase;
     sgs_run_kernel<<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds,
                                                                               iter0, n_steps, loss_cache, step_cache, blocks_cache,
                                                                               cache_stride, cache_offset, resampled, err_flag);
