@@ -9,8 +9,9 @@
 // pairwise order by rounding only (<= 1e-12 relative; the contract is 1e-9).
 //
 // Design (HBM-bound: 8 B read + 8 B written per cell per chain, everything else must stay on chip):
-//   * a CTA owns a 16 x 64 cell tile and loops over a group of chains; the five chain-independent fields of the tile
-//     (+halo) are staged ONCE in shared memory, so per chain only the bed is read from and the residual written to HBM;
+//   * a CTA owns an (RS_RW*RS_WARPS) x 64 cell tile and loops over a group of chains; the five chain-independent
+//     fields of the tile (+halo) are staged ONCE in shared memory and from there into each lane's registers, so per
+//     chain only the bed is read from and the residual written to HBM;
 //   * a warp owns RS_RW rows x 64 columns, a lane 2 adjacent columns: 16-byte accesses; x-neighbours come from warp
 //     shuffles, y-neighbours from the lane's own registers (the warp fetches its own halo rows);
 //   * the bed of the next chains streams in through a per-warp cp.async ring in shared memory (RS_STAGES-1 chains in
@@ -29,10 +30,10 @@
 #define RS_PITCH (RS_TW + 4)          // smem row pitch in doubles: [pad, haloL, 64 cells, haloR, pad] -> cells 16 B aligned
 #define RS_THREADS (RS_WARPS * 32)
 #ifndef RS_STAGES
-#define RS_STAGES 3                   // cp.async ring depth per warp
+#define RS_STAGES 4                   // cp.async ring depth per warp
 #endif
 #ifndef RS_MIN_CTAS
-#define RS_MIN_CTAS 4                 // 4 CTAs/SM: 46.7 KB of staged statics each, <= 128 registers per thread
+#define RS_MIN_CTAS 3                 // 3 CTAs/SM (<= 168 registers): the lane's statics live in registers, no spills
 #endif
 
 struct ResSmem {
@@ -88,28 +89,55 @@ __device__ __forceinline__ void fetch_bed(const LaneGeom& g, const double* __res
     }
 }
 
+// The lane's chain-independent operands, read once from the staged tile and then kept in registers for the whole chain
+// loop: with them in shared memory the kernel was shared-memory-bandwidth bound (73 % of the LSU wavefront peak).
+struct LaneStatics {
+    double2 sf[RS_RW + 2], vy[RS_RW + 2];     // surf, vely of rows i0-1 .. i0+RS_RW, the lane's two columns
+    double2 vx[RS_RW], dh[RS_RW], sm[RS_RW];  // velx, dhdt, smb of rows i0 .. i0+RS_RW-1
+    double hsf[RS_RW], hvx[RS_RW];            // surf, velx of the lane's halo column (lanes 0 and 31)
+    unsigned mcbits;                          // loss-mask bits: bit 2k (+1) = row k, first (second) column
+};
+
+__device__ __forceinline__ void load_statics(const ResSmem& S, const LaneGeom& g, LaneStatics& L) {
+    L.mcbits = 0;
+#pragma unroll
+    for (int k = 0; k < RS_RW + 2; ++k) {
+        L.sf[k] = *reinterpret_cast<const double2*>(&S.surf[g.wr0 + k][g.sc]);
+        L.vy[k] = *reinterpret_cast<const double2*>(&S.vely[g.wr0 + k][g.sc]);
+    }
+#pragma unroll
+    for (int k = 0; k < RS_RW; ++k) {
+        L.vx[k] = *reinterpret_cast<const double2*>(&S.velx[g.wr0 + k][g.sc]);
+        L.dh[k] = *reinterpret_cast<const double2*>(&S.dhdt[g.wr0 + k][g.sc]);
+        L.sm[k] = *reinterpret_cast<const double2*>(&S.smb[g.wr0 + k][g.sc]);
+        L.hsf[k] = S.surf[g.wr0 + k + 1][g.hsc];
+        L.hvx[k] = S.velx[g.wr0 + k][g.hsc];
+        const uchar2 m = *reinterpret_cast<const uchar2*>(&S.mc[g.wr0 + k][2 * g.lane]);
+        L.mcbits |= (m.x ? 1u : 0u) << (2 * k) | (m.y ? 1u : 0u) << (2 * k + 1);
+    }
+}
+
 // true when |x| lies in [2^-930, 2^930]: the FMA-corrected quotient is then free of over/underflow (see div_const)
 __device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
 
 template <bool WRITE_RES, bool DO_LOSS, bool VEC, bool INTERIOR>
-__device__ __forceinline__ void compute_rows(const GmcDev& d, const ResSmem& S, const LaneGeom& g,
+__device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics& L, const LaneGeom& g,
                                              const double (*bed)[RS_PITCH], double* __restrict__ out,
                                              double* __restrict__ partial, double r_res, double r_two_res) {
     // ---- fluxes: fy for rows -1..RS_RW, fx for rows 0..RS_RW-1 --------------------------------------------------
     double fy0[RS_RW + 2], fy1[RS_RW + 2], fx0[RS_RW], fx1[RS_RW], fxh[RS_RW];
 #pragma unroll
     for (int k = 0; k < RS_RW + 2; ++k) {
-        const double2 sf = *reinterpret_cast<const double2*>(&S.surf[g.wr0 + k][g.sc]);
-        const double2 vy = *reinterpret_cast<const double2*>(&S.vely[g.wr0 + k][g.sc]);
+        const double2 sf = L.sf[k], vy = L.vy[k];
         const double2 bd = *reinterpret_cast<const double2*>(&bed[k][g.sc]);
         const double t0 = sub_rn(sf.x, bd.x), t1 = sub_rn(sf.y, bd.y);
         fy0[k] = mul_rn(vy.x, t0);
         fy1[k] = mul_rn(vy.y, t1);
         if (k >= 1 && k <= RS_RW) {
-            const double2 vx = *reinterpret_cast<const double2*>(&S.velx[g.wr0 + k - 1][g.sc]);
+            const double2 vx = L.vx[k - 1];
             fx0[k - 1] = mul_rn(vx.x, t0);
             fx1[k - 1] = mul_rn(vx.y, t1);
-            fxh[k - 1] = mul_rn(S.velx[g.wr0 + k - 1][g.hsc], sub_rn(S.surf[g.wr0 + k][g.hsc], bed[k][g.hsc]));
+            fxh[k - 1] = mul_rn(L.hvx[k - 1], sub_rn(L.hsf[k - 1], bed[k][g.hsc]));
         }
     }
     // np.gradient's one-sided first/last rows as data: duplicating the edge row into the missing neighbour turns the
@@ -180,8 +208,7 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const ResSmem& S, 
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int k = kk + u;
-            const double2 dh = *reinterpret_cast<const double2*>(&S.dhdt[g.wr0 + k][g.sc]);
-            const double2 sm = *reinterpret_cast<const double2*>(&S.smb[g.wr0 + k][g.sc]);
+            const double2 dh = L.dh[k], sm = L.sm[k];
             const double r0 = sub_rn(add_rn(add_rn(quo[u][0], quo[u][2]), dh.x), sm.x);
             const double r1 = sub_rn(add_rn(add_rn(quo[u][1], quo[u][3]), dh.y), sm.y);
             if (INTERIOR || (((g.rowmask >> (k + 1)) & 1u) && g.v0)) {
@@ -194,9 +221,8 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const ResSmem& S, 
                     }
                 }
                 if (DO_LOSS) {
-                    const uchar2 m = *reinterpret_cast<const uchar2*>(&S.mc[g.wr0 + k][2 * g.lane]);
-                    if (m.x && r0 == r0) acc = add_rn(acc, mul_rn(r0, r0));
-                    if ((INTERIOR || g.v1) && m.y && r1 == r1) acc = add_rn(acc, mul_rn(r1, r1));
+                    if (((L.mcbits >> (2 * k)) & 1u) && r0 == r0) acc = add_rn(acc, mul_rn(r0, r0));
+                    if ((INTERIOR || g.v1) && ((L.mcbits >> (2 * k + 1)) & 1u) && r1 == r1) acc = add_rn(acc, mul_rn(r1, r1));
                 }
             }
         }
@@ -214,6 +240,8 @@ __device__ __forceinline__ void chain_loop(const GmcDev& d, ResSmem& S, const La
     const int G = gridDim.z;
     const int64_t cstride = (int64_t)G * plane, pstride = (int64_t)G * n_tiles;
     const int n_iter = (C - (int)blockIdx.z + G - 1) / G;          // chains blockIdx.z, +G, +2G, ...
+    LaneStatics L;
+    load_statics(S, g, L);
     // prologue: RS_STAGES-1 chains in flight (empty groups keep the group count uniform)
 #pragma unroll
     for (int s = 0; s < RS_STAGES - 1; ++s) {
@@ -228,7 +256,7 @@ __device__ __forceinline__ void chain_loop(const GmcDev& d, ResSmem& S, const La
         if (nxt < n_iter) fetch_bed<VEC, INTERIOR>(g, pb + (int64_t)nxt * cstride, S.ring[ns][warp]);
         cp_async_commit();
         cp_async_wait<RS_STAGES - 1>();                            // this lane's copies of chain `it` have landed
-        compute_rows<WRITE_RES, DO_LOSS, VEC, INTERIOR>(d, S, g, S.ring[stage][warp], po, pp, r_res, r_two_res);
+        compute_rows<WRITE_RES, DO_LOSS, VEC, INTERIOR>(d, L, g, S.ring[stage][warp], po, pp, r_res, r_two_res);
         if (WRITE_RES) po += cstride;
         pp += pstride;
         if (++stage == RS_STAGES) stage = 0;

@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-for v in "2 4 4 3" "2 4 3 4" "2 4 3 5" "4 4 2 3" "4 4 3 2" "2 8 2 3"; do
+for v in "2 4 4 3" "2 4 3 3" "2 4 3 4" "2 8 2 3" "4 4 2 3"; do
   set -- $v
   make -C mcmc_gpu_b200/csrc clean >/dev/null
   make -C mcmc_gpu_b200/csrc -j4 EXTRA="-DRS_RW=$1 -DRS_WARPS=$2 -DRS_MIN_CTAS=$3 -DRS_STAGES=$4" >/dev/null 2>&1 || { echo "build failed $v"; continue; }
@@ -9,4 +9,3 @@ for v in "2 4 4 3" "2 4 3 4" "2 4 3 5" "4 4 2 3" "4 4 3 2" "2 8 2 3"; do
 done
 make -C mcmc_gpu_b200/csrc clean >/dev/null; make -C mcmc_gpu_b200/csrc -j4 >/dev/null 2>&1
 python -m pytest tests/test_gpu_residual.py -m gpu -q 2>&1 | tail -2
-python profiles/stencil_only.py 256 500 2>&1 | head -3; python profiles/stencil_only.py 64 2000 5 | head -3
