@@ -294,45 +294,76 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
         // rho is needed again for the variance: keep a register copy in the first n threads
         const double rho_keep = (tid < n) ? S.rhs_a[tid] : 0.0;
         mark(3);
-        // (d) Gauss-Jordan elimination without pivoting (SPD block) on the augmented matrix [Sigma | rho | 1]: column p
-        // is cleared from every other row, so the system ends diagonal and no serial back substitution is needed.
-        // A warp owns rows wid, wid+8, ...; its lanes sweep the live columns p+1 .. n+1 (conflict-free, no index math).
+        // (d) Gauss-Jordan elimination without pivoting (SPD block) on the augmented matrix [Sigma | rho | 1], held in
+        // REGISTERS: thread (ty, tx) of a 16 x 16 layout owns rows ty+16a (a<4) and columns tx+16b (b<5) — a cyclic
+        // distribution, so the shrinking active region stays balanced.  Per pivot only the pivot row, the pivot column
+        // and 1/pivot travel through shared memory (double-buffered: one barrier per pivot); the n^3/2 multiply-adds run
+        // on registers with every lane busy.
         if (tid < n) {
             S.sig[tid * SGS_SIG_PITCH + n] = S.rhs_a[tid];
             S.sig[tid * SGS_SIG_PITCH + n + 1] = S.rhs_b[tid];
         }
         __syncthreads();
-        for (int p = 0; p < n; ++p) {
-            const double* prow = S.sig + p * SGS_SIG_PITCH;
-            const double inv = 1.0 / prow[p];
-            // the pivot row's live entries sit in registers (<= 3 per lane for n + 2 <= 66 columns); all loads of a row
-            // group are issued before the stores so the shared-memory round trips overlap instead of serialising
-            const int c0 = p + 1 + lane, c1 = c0 + 32, c2 = c0 + 64;
-            const double p0 = (c0 < n + 2) ? prow[c0] : 0.0, p1 = (c1 < n + 2) ? prow[c1] : 0.0, p2 = (c2 < n + 2) ? prow[c2] : 0.0;
-            constexpr int RG = 4;                                   // rows per group
-            for (int r0 = wid; r0 < n; r0 += RG * (SGS_THREADS / 32)) {
-                double f[RG], a0[RG], a1[RG], a2[RG];
+        {
+            const int ty = tid >> 4, tx = tid & 15;
+            double A[4][5];
 #pragma unroll
-                for (int q = 0; q < RG; ++q) {
-                    const int r = r0 + q * (SGS_THREADS / 32);
-                    const bool on = (r < n) && (r != p);
-                    const double* row = S.sig + (on ? r : p) * SGS_SIG_PITCH;
-                    f[q] = on ? row[p] * inv : 0.0;
-                    a0[q] = (c0 < n + 2) ? row[c0] : 0.0;
-                    a1[q] = (c1 < n + 2) ? row[c1] : 0.0;
-                    a2[q] = (c2 < n + 2) ? row[c2] : 0.0;
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 5; ++b2) {
+                    const int r = ty + 16 * a, c = tx + 16 * b2;
+                    A[a][b2] = (r < n && c < n + 2) ? S.sig[r * SGS_SIG_PITCH + c] : 0.0;
                 }
+            __syncthreads();                                 // S.sig is reused below as the exchange buffers
+            double* xrow = S.sig;                            // [2][80] pivot row, [2][64] pivot column, [2] 1/pivot
+            double* xcol = S.sig + 2 * 80;
+            double* xinv = S.sig + 2 * 80 + 2 * 64;
+            for (int p = 0; p < n; ++p) {
+                const int buf = p & 1, pa = p >> 4, pb = p >> 4, pty = p & 15, ptx = p & 15;
+                if (ty == pty) {                             // owners of the pivot row publish their entries
 #pragma unroll
-                for (int q = 0; q < RG; ++q) {
-                    const int r = r0 + q * (SGS_THREADS / 32);
-                    if ((r < n) && (r != p)) {
-                        double* row = S.sig + r * SGS_SIG_PITCH;
-                        if (c0 < n + 2) row[c0] = a0[q] - f[q] * p0;
-                        if (c1 < n + 2) row[c1] = a1[q] - f[q] * p1;
-                        if (c2 < n + 2) row[c2] = a2[q] - f[q] * p2;
-                    }
+                    for (int a = 0; a < 4; ++a)
+                        if (a == pa) {
+#pragma unroll
+                            for (int b2 = 0; b2 < 5; ++b2) xrow[buf * 80 + tx + 16 * b2] = A[a][b2];
+                            if (tx == ptx) {
+#pragma unroll
+                                for (int b2 = 0; b2 < 5; ++b2)
+                                    if (b2 == pb) xinv[buf] = 1.0 / A[a][b2];
+                            }
+                        }
+                }
+                if (tx == ptx) {                             // owners of the pivot column publish theirs
+#pragma unroll
+                    for (int b2 = 0; b2 < 5; ++b2)
+                        if (b2 == pb) {
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) xcol[buf * 64 + ty + 16 * a] = A[a][b2];
+                        }
+                }
+                __syncthreads();
+                const double inv = xinv[buf];
+                double pr[5];
+#pragma unroll
+                for (int b2 = 0; b2 < 5; ++b2) pr[b2] = xrow[buf * 80 + tx + 16 * b2];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int r = ty + 16 * a;
+                    const double f = (r != p) ? xcol[buf * 64 + r] * inv : 0.0;
+#pragma unroll
+                    for (int b2 = 0; b2 < 5; ++b2)
+                        if (tx + 16 * b2 > p) A[a][b2] -= f * pr[b2];
                 }
             }
+            __syncthreads();
+            // publish the diagonal and the two solved right-hand sides
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < 5; ++b2) {
+                    const int r = ty + 16 * a, c = tx + 16 * b2;
+                    if (r < n && (c == r || c == n || c == n + 1)) S.sig[r * SGS_SIG_PITCH + c] = A[a][b2];
+                }
             __syncthreads();
         }
         if (tid < n) {
