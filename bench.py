@@ -211,8 +211,8 @@ def gpu_main(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"          # the version banner goes to stdout; stdout carries ONE JSON line
+        # NCCL prints its version banner / debug lines to stdout; stdout carries ONE JSON line, so send them to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
