@@ -286,8 +286,13 @@ def gpu_main(a):
     peak, peak_src = measured_peak()
     launch_ms = float(np.mean(step_ms))
     achieved = bytes_last / (step_ms[-1] * 1e-3) / 1e9
+    # DRAM bytes per chain-step of this kernel from the committed ncu --set full capture (profiles/r1/run_kernel.ncu.txt:
+    # 757.8 MB read + 234.6 MB written over 256 chains x 40 iterations), scaled to this launch's chain-steps
+    ncu_traffic_per_chain_step = (757.827584e6 + 234.621440e6) / (256 * 40)
     roofline = {"kernel": "run_kernel (fused K1 field synthesis + K4 Metropolis step)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_chain_step * C * n_it,
+                "traffic_source": "profiles/r1/run_kernel.ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum per chain-step x chain-steps per launch)",
+                "algorithmic_bytes_per_launch": float(bytes_last), "peak_source": peak_src,
                 "algorithmic_bytes_per_chain_step": float(bytes_last) / (C * n_it), "launch_ms": launch_ms,
                 "note": "U3 block-local formulation; this kernel is FP64/shared-memory bound, not HBM bound (DESIGN.md)"}
 
