@@ -92,6 +92,11 @@ GMC_API int gmc_residual(gmc_ctx* ctx, const double* bed, double* res_out, int C
 GMC_API int gmc_residual_loss(gmc_ctx* ctx, const double* bed, double* res_out, double* loss_out, double* ssq_out, int C,
                       void* stream);
 
+/* Same for the chain range [chain0, chain0+C) of the context (pointers already point at that range): calls for disjoint
+ * ranges use disjoint workspace and may run concurrently on different streams (pipelined host<->device transfers). */
+GMC_API int gmc_residual_loss_range(gmc_ctx* ctx, const double* bed, double* res_out, double* loss_out, double* ssq_out,
+                                    int C, int chain0, void* stream);
+
 /* chain.loss (MCMC.py:1021-1044) on given residuals: res dev [C][H][W] -> loss_out dev [C] (ssq_out optional). */
 GMC_API int gmc_loss(gmc_ctx* ctx, const double* res, double* loss_out, double* ssq_out, int C, void* stream);
 

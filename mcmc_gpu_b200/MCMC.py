@@ -433,7 +433,7 @@ class chain_crf(chain):
         return out + ((sample_values,) if sample_values is not None else ())
 
     def run_many(self, n_iter, RF, initial_beds, rng_seeds, device=None, resync_every=4096, track_resampled=True,
-                 as_arrays=False, batch=None, out=None):
+                 as_arrays=False, batch=None, out=None, pipeline_groups=4):
         """Batched form: C independent chains (one per initial bed / seed) stepped concurrently on one GPU.
 
         Returns a list of the reference's 7-tuples (only_save_last_bed=True form), one per chain — what
@@ -445,6 +445,14 @@ class chain_crf(chain):
         if not isinstance(RF, RandField):
             raise TypeError('The arugment "RF" has to be an object of the class RandField')
         keys = [philox_key(s, s) for s in rng_seeds]
+        import torch
+        if (batch is not None and out is not None and isinstance(initial_beds, torch.Tensor) and initial_beds.is_pinned()
+                and pipeline_groups > 1):
+            # pinned host buffers on both sides: overlap the transfers with compute
+            res = batch.run_pipelined(initial_beds, keys, n_iter - 1, out, groups=pipeline_groups, resync_every=resync_every)
+            if as_arrays:
+                res["batch"] = batch
+                return res
         if batch is None:
             batch = ChainBatch(self, RF, initial_beds, keys, iter0=1, device=device, track_resampled=track_resampled)
         else:
@@ -574,7 +582,7 @@ class chain_sgs(chain):
         """n_iter block re-simulation proposals on the GPU; the reference's return tuple (MCMC.py:1599, 1897-1911).
 
         replay: optional sequence of dict(idx_x, idx_y, bsx, bsy, path[n,2], z[n], u) — the recorded random inputs of a
-        reference/oracle run, replayed through gmc_sgs_step_injected."""
+        reference run, replayed through gmc_sgs_step_injected."""
         if not hasattr(self, "rng_seed_int"):
             self.set_random_generator(None)
         H, W = self.xx.shape
@@ -811,6 +819,49 @@ class ChainBatch:
         blocks = bl.cpu().numpy().astype(np.float64)
         blocks[:, 0, :] = np.nan                      # MCMC.py:1169: row 0 of blocks_cache stays NaN
         return dict(bed=self.bed.cpu().numpy(), loss=lc.cpu().numpy(), steps=st.cpu().numpy(), blocks=blocks)
+
+    def run_pipelined(self, host_beds, keys, n_steps, out, groups=4, iter0=1, resync_every=4096):
+        """End-to-end run with host<->device transfers overlapped with compute: the chains are split into `groups` ranges,
+        each on its own CUDA stream (H2D of the beds -> residual+loss -> n_steps fused iterations -> D2H of the results).
+        The ranges start staggered by their H2D copies, so the D2H of one range overlaps the compute of the others.
+        host_beds / out[...] are pinned CPU tensors; results are identical to `reset` + `advance_into` (chains are
+        independent and counter-addressed)."""
+        torch = self.torch
+        if tuple(host_beds.shape) != (self.C, self.H, self.W) or host_beds.dtype != torch.float64:
+            raise GmcShapeError(f"initial beds must be float64 [{self.C},{self.H},{self.W}]")
+        n = n_steps + 1
+        lc, st, bl = self._device_caches(n)
+        self.seeds = keys_tensor(keys, self.dev)
+        den = torch.full((1,), 2 * self.chain.sigma_mc ** 2, dtype=torch.float64, device=self.dev)
+        if self.resampled is not None:
+            self.resampled.zero_()
+        groups = max(1, min(int(groups), self.C))
+        if not hasattr(self, "_streams") or len(self._streams) != groups:
+            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(groups)]
+        main = torch.cuda.current_stream()
+        bounds = [(g * self.C) // groups for g in range(groups + 1)]
+        for g, strm in enumerate(self._streams):
+            a, b = bounds[g], bounds[g + 1]
+            if a == b:
+                continue
+            strm.wait_stream(main)
+            with torch.cuda.stream(strm):
+                self.bed[a:b].copy_(host_beds[a:b], non_blocking=True)
+                self.ctx.residual_loss_range(self.bed[a:b], self.mcres[a:b], self._loss[a:b], self.ssq[a:b], a)
+                lc[a:b, 0] = self.ssq[a:b] / den
+                st[a:b, 0] = 0
+                bl[a:b, 0] = -1
+                self.ctx.run(self.bed[a:b], self.mcres[a:b], self.ssq[a:b], self.seeds[a:b], iter0, n_steps, lc[a:b], st[a:b],
+                             bl[a:b], 1, None if self.resampled is None else self.resampled[a:b], resync_every)
+                out["bed"][a:b].copy_(self.bed[a:b], non_blocking=True)
+                out["loss"][a:b].copy_(lc[a:b], non_blocking=True)
+                out["steps"][a:b].copy_(st[a:b], non_blocking=True)
+                out["blocks"][a:b].copy_(bl[a:b], non_blocking=True)
+        for strm in self._streams:
+            main.wait_stream(strm)
+        main.synchronize()
+        self.iteration = int(iter0) + n_steps
+        return dict(out)
 
     def step_injected(self, fields, centres, us):
         """One step per chain with injected proposals.  Returns (accepted[C] bool, loss[C])."""

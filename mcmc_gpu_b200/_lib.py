@@ -39,6 +39,7 @@ PROTOTYPES = {
     "gmc_set_blocks": (C.c_int, [_c_p, C.c_int, _c_p, _c_p, _c_p, _c_p, _f64]),
     "gmc_residual": (C.c_int, [_c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_residual_loss": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
+    "gmc_residual_loss_range": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, C.c_int, _c_p]),
     "gmc_loss": (C.c_int, [_c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_field_spectral": (C.c_int, [_c_p, C.c_int] + [_c_p] * 9 + [_u64, C.c_int, _c_p, _i64, _c_p]),
     "gmc_step_injected": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _i64, _c_p, _c_p, _c_p, C.c_int, C.c_int,
@@ -207,6 +208,10 @@ class Context:
     def residual_loss(self, bed, res_out, loss_out, ssq_out=None):
         check(self.lib.gmc_residual_loss(self._h, _ptr(bed), _ptr(res_out), _ptr(loss_out), _ptr(ssq_out), bed.shape[0],
                                          _stream()))
+
+    def residual_loss_range(self, bed, res_out, loss_out, ssq_out, chain0):
+        check(self.lib.gmc_residual_loss_range(self._h, _ptr(bed), _ptr(res_out), _ptr(loss_out), _ptr(ssq_out), bed.shape[0],
+                                               int(chain0), _stream()))
 
     def loss(self, res, loss_out, ssq_out=None):
         check(self.lib.gmc_loss(self._h, _ptr(res), _ptr(loss_out), _ptr(ssq_out), res.shape[0], _stream()))

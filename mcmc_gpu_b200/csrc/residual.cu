@@ -397,22 +397,25 @@ static int check_common(gmc_ctx* c, const void* p, int C, const char* who) {
 }
 
 template <bool WR, bool LS>
-static void launch_variant(gmc_ctx* c, dim3 grid, cudaStream_t st, const double* bed, double* res, int C, bool vec) {
+static void launch_variant(gmc_ctx* c, dim3 grid, cudaStream_t st, const double* bed, double* res, int C, bool vec, double* partials) {
     const double r_res = c->dev.r_res, r_two = c->dev.r_two_res;
     const size_t smem = sizeof(ResSmem);
     if (vec) {
         cudaFuncSetAttribute(residual_kernel<WR, LS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        residual_kernel<WR, LS, true><<<grid, RS_THREADS, smem, st>>>(c->dev, bed, res, c->d_partials, c->n_tiles, C, r_res, r_two);
+        residual_kernel<WR, LS, true><<<grid, RS_THREADS, smem, st>>>(c->dev, bed, res, partials, c->n_tiles, C, r_res, r_two);
     } else {
         cudaFuncSetAttribute(residual_kernel<WR, LS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        residual_kernel<WR, LS, false><<<grid, RS_THREADS, smem, st>>>(c->dev, bed, res, c->d_partials, c->n_tiles, C, r_res, r_two);
+        residual_kernel<WR, LS, false><<<grid, RS_THREADS, smem, st>>>(c->dev, bed, res, partials, c->n_tiles, C, r_res, r_two);
     }
 }
 
 static int launch_residual(gmc_ctx* c, const double* bed, double* res_out, double* loss_out, double* ssq_out, int C,
-                           bool do_loss, cudaStream_t st) {
+                           bool do_loss, cudaStream_t st, int chain0 = 0) {
     int rc = ensure_partials(c);
     if (rc) return rc;
+    // chain0 selects this call's rows of the partial-sum workspace, so calls for disjoint chain ranges may overlap on
+    // different streams
+    double* partials = c->d_partials + (size_t)chain0 * c->n_tiles;
     const int tx = tiles_x(c), ty = tiles_y(c);
     // chain groups: enough CTAs for ~8 per SM, but keep >= 8 chains per CTA to amortise the staged statics
     int groups = (24 * c->sm_count + tx * ty - 1) / (tx * ty);     // ~6 waves of 4 CTAs/SM: small tail
@@ -421,12 +424,12 @@ static int launch_residual(gmc_ctx* c, const double* bed, double* res_out, doubl
     const dim3 grid(tx, ty, groups);
     // 16-byte accesses need even W and 16 B aligned bases
     const bool vec = (c->W % 2 == 0) && ((uintptr_t)bed % 16 == 0) && (!res_out || (uintptr_t)res_out % 16 == 0);
-    if (res_out && do_loss) launch_variant<true, true>(c, grid, st, bed, res_out, C, vec);
-    else if (res_out) launch_variant<true, false>(c, grid, st, bed, res_out, C, vec);
-    else launch_variant<false, true>(c, grid, st, bed, res_out, C, vec);
+    if (res_out && do_loss) launch_variant<true, true>(c, grid, st, bed, res_out, C, vec, partials);
+    else if (res_out) launch_variant<true, false>(c, grid, st, bed, res_out, C, vec, partials);
+    else launch_variant<false, true>(c, grid, st, bed, res_out, C, vec, partials);
     c->launches++;
     if (do_loss) {
-        finalize_loss_kernel<<<(C + 7) / 8, 256, 0, st>>>(c->d_partials, c->n_tiles, c->dev.two_sigma2, loss_out, ssq_out, C);
+        finalize_loss_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, c->n_tiles, c->dev.two_sigma2, loss_out, ssq_out, C);
         c->launches++;
     }
     GMC_CUDA(cudaGetLastError());
@@ -446,6 +449,16 @@ extern "C" int gmc_residual_loss(gmc_ctx* c, const double* bed, double* res_out,
     if (rc) return rc;
     if (!loss_out && !ssq_out) GMC_FAIL(GMC_EINVAL, "gmc_residual_loss: loss_out and ssq_out are both NULL");
     return launch_residual(c, bed, res_out, loss_out, ssq_out, C, true, (cudaStream_t)stream);
+}
+
+extern "C" int gmc_residual_loss_range(gmc_ctx* c, const double* bed, double* res_out, double* loss_out, double* ssq_out,
+                                       int C, int chain0, void* stream) {
+    int rc = check_common(c, bed, C, "gmc_residual_loss_range");
+    if (rc) return rc;
+    if (!loss_out && !ssq_out) GMC_FAIL(GMC_EINVAL, "gmc_residual_loss_range: loss_out and ssq_out are both NULL");
+    if (chain0 < 0 || chain0 + C > c->max_chains)
+        GMC_FAIL(GMC_ESHAPE, "gmc_residual_loss_range: chains [%d,%d) outside the context's capacity %d", chain0, chain0 + C, c->max_chains);
+    return launch_residual(c, bed, res_out, loss_out, ssq_out, C, true, (cudaStream_t)stream, chain0);
 }
 
 extern "C" int gmc_loss(gmc_ctx* c, const double* res, double* loss_out, double* ssq_out, int C, void* stream) {
