@@ -187,6 +187,14 @@ GMC_API int gmc_ensemble_moments(gmc_ctx* ctx, const double* bed, const double* 
  * collective on the path).  libnccl.so.2 is resolved at run time from the process (torch ships it). */
 GMC_API int gmc_allreduce_moments(gmc_ctx* ctx, void* nccl_comm, double* sum, double* sumsq, double* count, void* stream);
 
+/* ---- setup helper ------------------------------------------------------------------------------------------------ */
+
+/* Utilities.min_dist_from_mask (Utilities.py:21-24): out[q] = min_p sqrt((qx-px)^2 + (qy-py)^2), bit-identical to the
+ * reference's KD-tree query.  All pointers dev.  Used for the block tapers (MCMC.py:583-623) and the conditioning weight
+ * (MCMC.py:689-714).  Brute force, O(N*M). */
+GMC_API int gmc_min_dist(int device, const double* px, const double* py, int64_t M, const double* qx, const double* qy,
+                         int64_t N, double* out, void* stream);
+
 /* ---- introspection for tests and bench ---------------------------------------------------------------------- */
 
 /* Number of kernel launches issued through this context since creation. */

@@ -135,11 +135,16 @@ class RandField:
 
     def get_crf_weight(self, xx, yy, cond_data_mask):
         """(weight, dist, dist_rescale, dist_logi): conditioning weight, 0 at data cells (MCMC.py:689-714).
-        One-time setup, outside the hot path; the nearest-data distance uses scipy's KD-tree like the reference."""
-        from scipy.spatial import cKDTree
+        One-time setup, outside the hot path; the nearest-data distance is an exact scan on the GPU (Utilities.py)."""
         sel = np.asarray(cond_data_mask) == 1
-        tree = cKDTree(np.column_stack([xx[sel], yy[sel]]))
-        dist = tree.query(np.column_stack([xx.ravel(), yy.ravel()]))[0].reshape(xx.shape)
+        import torch
+        if torch.cuda.is_available():
+            from .Utilities import min_dist_from_mask            # exact GPU scan, bit-identical to the KD-tree query
+            dist = min_dist_from_mask(np.asarray(xx), np.asarray(yy), sel)
+        else:                                                    # setup on a GPU-less host (e.g. preparing inputs)
+            from scipy.spatial import cKDTree
+            tree = cKDTree(np.column_stack([xx[sel], yy[sel]]))
+            dist = tree.query(np.column_stack([xx.ravel(), yy.ravel()]))[0].reshape(xx.shape)
         return self.get_crf_weight_from_dist(xx, yy, dist)
 
     def get_crf_weight_from_dist(self, xx, yy, dist):

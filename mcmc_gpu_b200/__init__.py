@@ -5,11 +5,11 @@ Importing the package does not need a GPU; any computation does (no CPU fallback
 """
 from . import synthetic  # noqa: F401
 
-__all__ = ["MCMC", "Topography", "synthetic", "drivers"]
+__all__ = ["MCMC", "Topography", "Utilities", "synthetic", "drivers"]
 
 
 def __getattr__(name):
-    if name in ("MCMC", "Topography", "drivers", "_lib"):
+    if name in ("MCMC", "Topography", "Utilities", "drivers", "_lib", "sgs_tables"):
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

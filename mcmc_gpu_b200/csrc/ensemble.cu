@@ -88,3 +88,42 @@ extern "C" int gmc_allreduce_moments(gmc_ctx* c, void* comm, double* sum, double
     if (rc || rc2) GMC_FAIL(GMC_ENCCL, "gmc_allreduce_moments: NCCL error: %s", es(rc ? rc : rc2));
     return GMC_OK;
 }
+
+// ---- setup helper: exact distance to the nearest masked point ----------------------------------------
+// Utilities.min_dist_from_mask (Utilities.py:21-24) queries a KD-tree; the answer is min_p sqrt((x-px)^2 + (y-py)^2) with
+// each operation rounded separately (no FMA), which a brute-force scan reproduces bit-for-bit.  Points are tiled through
+// shared memory; one thread per query.  O(N*M): meant for the block tapers and conditioning weights (M = radar cells).
+__global__ void __launch_bounds__(256)
+    min_dist_kernel(const double* __restrict__ px, const double* __restrict__ py, int64_t M, const double* __restrict__ qx,
+                    const double* __restrict__ qy, int64_t N, double* __restrict__ out) {
+    __shared__ double sx[1024], sy[1024];
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const double x = (q < N) ? qx[q] : 0.0, y = (q < N) ? qy[q] : 0.0;
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    for (int64_t base = 0; base < M; base += 1024) {
+        const int n = (int)((M - base < 1024) ? M - base : 1024);
+        __syncthreads();
+        for (int t = threadIdx.x; t < n; t += blockDim.x) {
+            sx[t] = px[base + t];
+            sy[t] = py[base + t];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int t = 0; t < n; ++t) {
+            const double dx = __dsub_rn(x, sx[t]), dy = __dsub_rn(y, sy[t]);
+            const double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            best = fmin(best, d2);
+        }
+    }
+    if (q < N) out[q] = sqrt(best);
+}
+
+extern "C" int gmc_min_dist(int device, const double* px, const double* py, int64_t M, const double* qx, const double* qy,
+                            int64_t N, double* out, void* stream) {
+    if (!px || !py || !qx || !qy || !out) GMC_FAIL(GMC_EINVAL, "gmc_min_dist: NULL argument");
+    if (M < 1 || N < 1) GMC_FAIL(GMC_EINVAL, "gmc_min_dist: empty point or query set");
+    GMC_CUDA(cudaSetDevice(device));
+    min_dist_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(px, py, M, qx, qy, N, out);
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}

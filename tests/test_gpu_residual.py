@@ -122,3 +122,18 @@ def test_division_by_constant_is_correctly_rounded(divisor):
     ])
     xd = torch.as_tensor(x).cuda()
     assert ctx.div_check(xd, divisor) == 0
+
+
+def test_min_dist_from_mask_is_bit_identical_to_the_kdtree():
+    """Utilities.min_dist_from_mask on the GPU vs the reference's KD-tree query (Utilities.py:21-24)."""
+    from scipy.spatial import KDTree
+    from mcmc_gpu_b200 import Utilities
+    g = np.random.default_rng(3)
+    for (H, W, res, frac) in [(64, 80, 500.0, 0.02), (37, 53, 0.1, 0.3), (120, 90, 123.456, 0.001)]:
+        xx, yy = np.meshgrid(np.arange(W) * res, np.arange(H) * res * 0.7)
+        mask = g.random((H, W)) < frac
+        mask[H // 2, W // 2] = True
+        tree = KDTree(np.array([xx[mask], yy[mask]]).T)
+        ref = tree.query(np.array([xx.ravel(), yy.ravel()]).T)[0].reshape(xx.shape)
+        got = Utilities.min_dist_from_mask(xx, yy, mask)
+        assert np.array_equal(got, ref), (H, W)
