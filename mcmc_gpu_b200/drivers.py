@@ -57,6 +57,11 @@ def seed_folder(output_path, seed) -> Path:
     return Path(output_path) / "LargeScaleChain" / f"{str(seed)[:6]}"
 
 
+def ssc_seed_folder(output_path, lsc_seed, ssc_seed) -> Path:
+    """Folder of one small-scale chain below its parent large-scale chain (largeScaleChain_multiprocessing.py:289)."""
+    return Path(output_path) / "LargeScaleChain" / f"{str(lsc_seed)[:6]}" / "SmallScaleChain" / f"{str(ssc_seed)[:6]}"
+
+
 def load_checkpoint(folder: Path):
     """Returns None or dict(cumulative_iters, bed, previous results, rng state) like lsc_run_wrapper's resume branch."""
     marker = folder / "current_iter.txt"
@@ -162,6 +167,58 @@ def largeScaleChain_mp(n_chains, n_workers, largeScaleChain, rf, initial_beds, r
                 save_checkpoint(seed_folder(output_path, rng_seeds[i]), res, prev, cum, n_iter, key, it0 + n_iter - 1)
     if verbose and rank == 0:
         print(f"Completed in {time.time() - tic:.2f} seconds")
+    return [results[i] for i in mine]
+
+
+def sgs_gpu_runner(chain_obj, _unused, beds, keys, iter0s, n_iter, device=None):
+    """Run len(beds) small-scale chains for n_iter block re-simulations on this rank's GPU (kernel K6)."""
+    out = [None] * len(beds)
+    for it0 in sorted(set(iter0s)):
+        sel = [i for i, v in enumerate(iter0s) if v == it0]
+        batch = MCMC.SgsBatch(chain_obj, np.stack([beds[i] for i in sel]), [keys[i] for i in sel], iter0=it0, device=device)
+        lc, st, bl = batch.advance(n_iter)
+        last = batch.beds(with_trend=True)
+        resampled = batch.resampled_times()
+        for j, i in enumerate(sel):
+            loss = np.array(lc[j], dtype=np.float64)
+            out[i] = (np.array(last[j]), loss.copy(), np.zeros(n_iter), loss, np.array(st[j], dtype=np.float64), resampled[j],
+                      np.array(bl[j], dtype=np.float64))
+        batch.close()
+    return out
+
+
+def smallScaleChain_mp(n_chains, n_workers, smallScaleChain, initial_beds, ssc_rng_seeds, lsc_rng_seed, n_iters,
+                       output_path="./Data/output", *, runner=None, device=None, save=True, verbose=True):
+    """Drop-in for the reference's smallScaleChain_mp (largeScaleChain_multiprocessing.py:243-318): same positional
+    signature, same 7-tuples, same files under <output>/LargeScaleChain/<lsc seed>/SmallScaleChain/<ssc seed>/.
+    All chains of a rank advance in one kernel launch; ranks (torch.distributed) take contiguous shards of the chains."""
+    rank, world = dist_info()
+    mine = shard_chains(n_chains, world, rank)
+    runner = runner or (lambda *a: sgs_gpu_runner(*a, device=device))
+    tic = time.time()
+    results = {}
+    for n_iter in sorted({int(n_iters[i]) for i in mine}):
+        group = [i for i in mine if int(n_iters[i]) == n_iter]
+        beds, keys, iter0s, prevs, cums = [], [], [], [], []
+        for i in group:
+            folder = ssc_seed_folder(output_path, lsc_rng_seed, ssc_rng_seeds[i])
+            prev = load_checkpoint(folder) if save else None
+            key, it0 = MCMC.philox_key(ssc_rng_seeds[i]), 0
+            bed = np.asarray(initial_beds[i], dtype=np.float64)
+            if prev is not None:
+                bed = prev["bed"]
+                if prev["rng"] is not None:
+                    key, it0 = int(prev["rng"]["key"]), int(prev["rng"]["iteration"])
+            beds.append(bed); keys.append(key); iter0s.append(it0); prevs.append(prev)
+            cums.append(0 if prev is None else prev["cumulative_iters"])
+        outs = runner(smallScaleChain, None, beds, keys, iter0s, n_iter)
+        for i, res, prev, cum, key, it0 in zip(group, outs, prevs, cums, keys, iter0s):
+            results[i] = res
+            if save:
+                save_checkpoint(ssc_seed_folder(output_path, lsc_rng_seed, ssc_rng_seeds[i]), res, prev, cum, n_iter, key,
+                                it0 + n_iter)
+    if verbose and rank == 0:
+        print(f"Completed in {time.time() - tic} seconds")
     return [results[i] for i in mine]
 
 

@@ -87,3 +87,25 @@ def test_public_run_api_free_rng():
     assert beds.shape == (12,) + g["bed_init"].shape and loss.shape == (12,) and blocks.shape == (12, 4)
     changed = [not np.array_equal(beds[i], beds[i - 1]) for i in range(1, 12)]
     assert np.array_equal(np.array(changed), steps[1:].astype(bool))
+
+
+def test_small_scale_driver_layout_and_resume(tmp_path):
+    """smallScaleChain_mp on the GPU: the reference's folder layout; two runs of 6 == one uninterrupted run of 12."""
+    from mcmc_gpu_b200 import MCMC, drivers
+    case = SGS_CASES["matern_nst"]
+    ch, g = product_sgs_chain(case)
+    seeds, lsc = [901, 902], 777
+    beds0 = [g["bed_init"], g["bed_init"] + 0.2]
+    r1 = quiet(drivers.smallScaleChain_mp, 2, 4, ch, beds0, seeds, lsc, [6, 6], str(tmp_path))
+    r2 = quiet(drivers.smallScaleChain_mp, 2, 4, ch, beds0, seeds, lsc, [6, 6], str(tmp_path))
+    folder = tmp_path / "LargeScaleChain" / "777" / "SmallScaleChain" / "901"
+    assert sorted(p.name for p in folder.iterdir()) == ["RNGState_RandField.txt", "RNGState_chain.txt", "bed_0k.npy",
+                                                        "current_iter.txt", "results_0k.npz"]
+    assert int(np.loadtxt(folder / "current_iter.txt")) == 12
+    batch = MCMC.SgsBatch(ch, np.stack(beds0), [MCMC.philox_key(s) for s in seeds])
+    batch.advance(12)
+    final = batch.beds(with_trend=True)
+    for k in range(2):
+        # resume re-derives bedc = bed - trend from the saved full bed: one rounding of (x + t) - t per cell
+        assert np.abs(final[k] - r2[k][0]).max() <= 1e-9 * np.abs(final[k]).max()
+        assert len(r1[k]) == 7 and r1[k][3].shape == (6,)
