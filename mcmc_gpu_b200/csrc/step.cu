@@ -270,6 +270,41 @@ __device__ __noinline__ double spec_amp(const SpecParams& sp, double ksq_sum) {
     return sqrt(S);
 }
 
+// One spectrum item of the device-RNG path: sqrt(S) and the two complex normals of its mirrored rows.  A single
+// out-of-line body (one copy in the instruction cache) in which the three dependency chains — log/exp of the density,
+// log/sqrt/sincospi of the two Box-Muller draws — are independent, so the scheduler interleaves them.
+struct FillItem {
+    double amp, z0, z1, y0, y1;
+};
+__device__ __forceinline__ double spec_density(const SpecParams& sp, double ksq_sum) {
+    const double k = add_rn(sqrt(ksq_sum), 1e-10);
+    if (sp.model == GMC_GAUSSIAN) {
+        const double ak = mul_rn(sp.a, k);
+        return exp(mul_rn(-0.5, mul_rn(ak, ak)));
+    }
+    if (sp.model == GMC_EXPONENTIAL) {
+        const double ak = mul_rn(sp.a, k);
+        return div_rn(1.0, pow_pos(add_rn(1.0, mul_rn(ak, ak)), 1.5));
+    }
+    const double four_pi = 4 * 3.141592653589793;
+    return mul_rn(sp.constant, pow_pos(add_rn(sp.kappa, mul_rn(four_pi, mul_rn(k, k))), sub_rn(-sp.nu, 1.0)));
+}
+__device__ __noinline__ void fill_item(const SpecParams& sp, const Philox& rng, uint32_t it_lo, uint32_t it_hi, double ks,
+                                       uint32_t e0, uint32_t e1, FillItem& r) {
+    const uint4 a = rng(e0, it_lo, it_hi, GMC_STREAM_NOISE), b = rng(e1, it_lo, it_hi, GMC_STREAM_NOISE);
+    const double l0 = log(u01_open(a.x, a.y)), l1 = log(u01_open(b.x, b.y));
+    double s0, c0, s1, c1;
+    sincospi(2.0 * u01_open(a.z, a.w), &s0, &c0);
+    sincospi(2.0 * u01_open(b.z, b.w), &s1, &c1);
+    const double S = spec_density(sp, ks);
+    const double q0 = sqrt(-2.0 * l0), q1 = sqrt(-2.0 * l1);
+    r.amp = sqrt(S);
+    r.z0 = q0 * c0;
+    r.z1 = q0 * s0;
+    r.y0 = q1 * c1;
+    r.y1 = q1 * s1;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K1: synthesise one field into shared memory.  On return (after its final __syncthreads) the standardised field times
 // `scale` sits in buf as F[y * fpitch + x] with fpitch = 2 * pitchc doubles (rows are the complex rows of the half plane).
@@ -351,39 +386,46 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
     // variance (Parseval): interior columns count twice (their mirror images kx > w/2 are not stored).
     double power = 0.0;
     const FastDiv dhc(hc);
-    for (int q = threadIdx.x; q < (h / 2 + 1) * hc; q += GMC_STEP_THREADS) {
-        const int a = dhc.div(q), kx = q - a * hc;
-        // MCMC.py:224: k = sqrt(kxv**2 + kyv**2) + 1e-10
-        const double amp = spec_amp(sp, add_rn(ksqX[kx], ksqY[a]));
+    const int n_items = (h / 2 + 1) * hc;
+    // store one item's (up to) two entries and accumulate their power
+    auto emit = [&](int a, int kx, double2 X0, double2 X1) {
         const bool self_y = (a == 0 || 2 * a == h);
         const bool edge_x = (kx == 0 || kx == n2);
-        const int a2 = self_y ? a : h - a;
-        double2 X0, X1;
-        if (INJECT) {
-            // X_h(k) = sqrt(S)/2 * ((A_k + A_-k) + i (B_k - B_-k)),  -k = ((h-ky)%h, (w-kx)%w)
-            const int kxm = (kx == 0) ? 0 : w - kx;
-            const int e0 = a * w + kx, m0 = ((a == 0) ? 0 : h - a) * w + kxm;
-            const int e1 = a2 * w + kx, m1 = ((a2 == 0) ? 0 : h - a2) * w + kxm;
-            X0 = make_double2(0.5 * amp * (z_re[e0] + z_re[m0]), 0.5 * amp * (z_im[e0] - z_im[m0]));
-            X1 = make_double2(0.5 * amp * (z_re[e1] + z_re[m1]), 0.5 * amp * (z_im[e1] - z_im[m1]));
-        } else {
-            // straight-line: both draws and sqrt(S) are independent dependency chains the scheduler can interleave
-            // (the second draw is unused for self-conjugate rows / Hermitian columns: < 10 % of the items)
-            double z0, z1, y0, y1;
-            box_muller(rng((uint32_t)(a * w + kx), it_lo, it_hi, GMC_STREAM_NOISE), z0, z1);
-            box_muller(rng((uint32_t)(a2 * w + kx), it_lo, it_hi, GMC_STREAM_NOISE), y0, y1);
-            const double am = amp * inv_sqrt2;
-            const bool real_pt = self_y && edge_x;                 // self-conjugate point: real, variance S
-            X0 = make_double2(real_pt ? amp * z0 : am * z0, real_pt ? 0.0 : am * z1);
-            X1 = edge_x ? cconj(X0) : make_double2(am * y0, am * y1);   // columns kx = 0, w/2 are Hermitian in ky
-        }
         if (a == 0 && kx == 0) X0 = X1 = make_double2(0.0, 0.0);   // DC: removed by the mean subtraction (MCMC.py:248)
         const double wgt = edge_x ? 1.0 : 2.0;
         power += wgt * (X0.x * X0.x + X0.y * X0.y);
         Z[posY[a] * pitchc + kx] = X0;
         if (!self_y) {
             power += wgt * (X1.x * X1.x + X1.y * X1.y);
-            Z[posY[a2] * pitchc + kx] = X1;
+            Z[posY[h - a] * pitchc + kx] = X1;
+        }
+    };
+    if (INJECT) {
+        for (int q = threadIdx.x; q < n_items; q += GMC_STEP_THREADS) {
+            const int a = dhc.div(q), kx = q - a * hc;
+            // MCMC.py:224: k = sqrt(kxv**2 + kyv**2) + 1e-10
+            const double amp = spec_amp(sp, add_rn(ksqX[kx], ksqY[a]));
+            const int a2 = (a == 0 || 2 * a == h) ? a : h - a;
+            // X_h(k) = sqrt(S)/2 * ((A_k + A_-k) + i (B_k - B_-k)),  -k = ((h-ky)%h, (w-kx)%w)
+            const int kxm = (kx == 0) ? 0 : w - kx;
+            const int e0 = a * w + kx, m0 = ((a == 0) ? 0 : h - a) * w + kxm;
+            const int e1 = a2 * w + kx, m1 = ((a2 == 0) ? 0 : h - a2) * w + kxm;
+            emit(a, kx, make_double2(0.5 * amp * (z_re[e0] + z_re[m0]), 0.5 * amp * (z_im[e0] - z_im[m0])),
+                 make_double2(0.5 * amp * (z_re[e1] + z_re[m1]), 0.5 * amp * (z_im[e1] - z_im[m1])));
+        }
+    } else {
+        // the second draw of an item is unused for self-conjugate rows / Hermitian columns (< 10 % of the items)
+        for (int q = threadIdx.x; q < n_items; q += GMC_STEP_THREADS) {
+            const int a = dhc.div(q), kx = q - a * hc;
+            const bool self_y = (a == 0 || 2 * a == h), edge_x = (kx == 0 || kx == n2);
+            const int a2 = self_y ? a : h - a;
+            FillItem fi;
+            fill_item(sp, rng, it_lo, it_hi, add_rn(ksqX[kx], ksqY[a]), (uint32_t)(a * w + kx), (uint32_t)(a2 * w + kx), fi);
+            const double am = fi.amp * inv_sqrt2;
+            const bool real_pt = self_y && edge_x;                 // self-conjugate point: real, variance S
+            const double2 X0 = make_double2(real_pt ? fi.amp * fi.z0 : am * fi.z0, real_pt ? 0.0 : am * fi.z1);
+            const double2 X1 = edge_x ? cconj(X0) : make_double2(am * fi.y0, am * fi.y1);   // kx = 0, w/2: Hermitian in ky
+            emit(a, kx, X0, X1);
         }
     }
     power = block_sum<GMC_STEP_THREADS>(power, scratch);           // also orders the fill before the column pass
