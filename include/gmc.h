@@ -113,6 +113,28 @@ GMC_API int gmc_field_spectral(gmc_ctx* ctx, int n, const int32_t* pair, const d
                        const double* z_nug, const uint64_t* seeds, uint64_t iter, int apply_taper, double* f_out,
                        int64_t stride, void* stream);
 
+/* RandField.set_generation_method (MCMC.py:514-522).  spectral != 0 (default): gmc_run proposes with the FFT synthesis
+ * (A3).  spectral == 0: with the randomization method (A5, below) using n_modes wave vectors per field (gstools SRF
+ * default mode_no = 1000). */
+GMC_API int gmc_set_generation_method(gmc_ctx* ctx, int spectral, int n_modes);
+
+/* A5 — RandField.get_random_field (MCMC.py:625-687: gstools.SRF(model).structured([X, Y]).T * scale), n fields:
+ *   field[y][x] = scale * ( sqrt(1/n_modes) * sum_m [ z1_m cos(kx_m x res + ky_m y res) + z2_m sin(..) ] + sqrt(nug) n[y][x] )
+ * (times the edge taper of get_rfblock when apply_taper).
+ *   pair[n] i32 dev : block-size index;  scale[n], nug[n], range_x[n], range_y[n], angle_deg[n] f64 dev : the sampled
+ *                     parameters (scale already / 3; gstools len_scale = range / sqrt(3) | 3 | 2 by model, angle in degrees)
+ *   modes           : dev [n][n_modes][4] = (kx, ky, z1, z2), wave vectors in the grid frame (rad per unit of the
+ *                     field resolution), with z_nug dev [n][stride] unit normals — or both NULL: wave vectors are drawn
+ *                     on the device from the model's radial spectral distribution (closed-form inversion in 2-D, see
+ *                     DESIGN.md) and Philox streams keyed by seeds[n] (u64 dev) at iteration `iter`
+ *   f_out           : dev [n][stride], field i row-major [pair_h][pair_w] at f_out + i*stride
+ * gstools (1.7.0 in the reference environment) is not vendored and its RNG is unseeded in the reference: parity of
+ * this branch is unpinned; the summation is checked against oracle/randmeth_oracle.py, the sampling distributionally. */
+GMC_API int gmc_field_randmeth(gmc_ctx* ctx, int n, const int32_t* pair, const double* scale, const double* nug,
+                       const double* range_x, const double* range_y, const double* angle_deg, int n_modes,
+                       const double* modes, const double* z_nug, const uint64_t* seeds, uint64_t iter, int apply_taper,
+                       double* f_out, int64_t stride, void* stream);
+
 /* ---- A6: Metropolis step ------------------------------------------------------------------------------------ */
 
 /* One chain_crf.run loop body (MCMC.py:1263-1360) for C chains with the proposal injected:

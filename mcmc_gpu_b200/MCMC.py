@@ -84,10 +84,13 @@ class RandField:
         self._draws = 0          # Philox iteration counter of stand-alone get_rfblock() calls
         self._ctx = None
 
-    def set_generation_method(self, spectral):
-        """True: FFT spectral synthesis (the only method on the GPU path).  The reference's other branch calls the
-        un-vendored gstools RandMeth generator with an unseeded RNG (MCMC.py:625-687)."""
+    def set_generation_method(self, spectral, n_modes=1000):
+        """True: FFT spectral synthesis (A3).  False: the gstools randomization method of `get_random_field`
+        (MCMC.py:625-687) with `n_modes` wave vectors (gstools SRF default mode_no=1000), generated on the GPU."""
         self.spectral = spectral
+        self.n_modes = int(n_modes)
+        if self._ctx is not None:
+            self._ctx.set_generation_method(bool(spectral), self.n_modes)
 
     def set_block_sizes(self, min_block_x, max_block_x, min_block_y, max_block_y, steps=5):
         self.min_block_x, self.max_block_x = min_block_x, max_block_x
@@ -164,37 +167,65 @@ class RandField:
             self._ctx = ctx
         return self._ctx
 
-    def _require_spectral(self):
-        if not getattr(self, "spectral", True):
-            raise NotImplementedError("spectral=False selects the gstools RandMeth generator (MCMC.py:625-687), which is "
-                                      "an un-vendored dependency with an unseeded RNG in the reference; only the spectral "
-                                      "method is implemented on the GPU path")
-
-    def get_rfblock(self):
-        """One tapered proposal field f = field * edge_mask (MCMC.py:742-778), synthesised by kernel K1."""
-        import torch
-        self._require_spectral()
-        ctx = self._field_ctx()
-        dev = ctx.device
+    def _draw_field_params(self):
+        """scale, nug, range1, range2, angle in the reference's draw order (MCMC.py:200-207 / 642-653)."""
         g = self.rng
-        pick = int(g.integers(low=0, high=self.pairs.shape[1], size=1)[0])
         scale = g.uniform(self.scale_min, self.scale_max) / 3.0
         nug = g.uniform(0.0, self.nugget_max)
+        angle = 0.0
         if not self.isotropic:
             rx = g.uniform(self.range_min_x, self.range_max_x)
             ry = g.uniform(self.range_min_y, self.range_max_y)
+            if not getattr(self, "spectral", True):
+                angle = g.uniform(0, 180)
         else:
             rx = ry = g.uniform(self.range_min_x, self.range_max_x)
-        bw, bh = int(self.pairs[0, pick]), int(self.pairs[1, pick])
+        return scale, nug, rx, ry, angle
+
+    def _generate(self, ctx, pick, bh, bw, apply_taper):
+        import torch
+        dev = ctx.device
+        scale, nug, rx, ry, angle = self._draw_field_params()
         out = torch.empty((1, ctx.max_h * ctx.max_w), dtype=torch.float64, device=dev)
 
         def t(v, dt=torch.float64):
             return torch.tensor([v], dtype=dt, device=dev)
         seeds = keys_tensor([philox_key(self.rng_seed_int)], dev)
-        ctx.field_spectral(t(pick, torch.int32), t(scale), t(nug), t(rx), t(ry), out, seeds=seeds, iteration=self._draws,
-                           apply_taper=True)
+        if getattr(self, "spectral", True):
+            ctx.field_spectral(t(pick, torch.int32), t(scale), t(nug), t(rx), t(ry), out, seeds=seeds,
+                               iteration=self._draws, apply_taper=apply_taper)
+        else:
+            ctx.field_randmeth(t(pick, torch.int32), t(scale), t(nug), t(rx), t(ry), t(angle), out,
+                               n_modes=getattr(self, "n_modes", 1000), seeds=seeds, iteration=self._draws,
+                               apply_taper=apply_taper)
         self._draws += 1
         return out[0, :bh * bw].reshape(bh, bw).cpu().numpy()
+
+    def get_random_field(self, X, Y, n=1):
+        """One realisation [len(Y), len(X)] of the randomization-method generator (MCMC.py:625-687: gstools
+        SRF(model).structured([X, Y]).T * scale), summed on the GPU (A5).  Like the reference, only the first of the
+        `n` realisations is returned, and X, Y are taken as regular axes starting at 0."""
+        X, Y = np.asarray(X, dtype=np.float64), np.asarray(Y, dtype=np.float64)
+        nx, ny = len(X), len(Y)
+        res = float(X[1] - X[0]) if nx > 1 else float(getattr(self, "resolution", 1.0))
+        ctx = Context(max(ny, 2), max(nx, 2), 1)
+        ctx.set_field_model(self.model_name, self.smoothness, self.isotropic, self.range_min_x, self.range_max_x,
+                            self.range_min_y, self.range_max_y, self.scale_min, self.scale_max, self.nugget_max)
+        ctx.set_blocks(np.array([[nx], [ny]]), [np.ones((ny, nx))], res)
+        spectral, self.spectral = getattr(self, "spectral", True), False
+        try:
+            return self._generate(ctx, 0, ny, nx, apply_taper=False)
+        finally:
+            self.spectral = spectral
+            ctx.close()
+
+    def get_rfblock(self):
+        """One tapered proposal field f = field * edge_mask (MCMC.py:742-778), synthesised by kernel K1 (spectral) or
+        the randomization-method kernel (set_generation_method(False))."""
+        ctx = self._field_ctx()
+        pick = int(self.rng.integers(low=0, high=self.pairs.shape[1], size=1)[0])
+        bw, bh = int(self.pairs[0, pick]), int(self.pairs[1, pick])
+        return self._generate(ctx, pick, bh, bw, apply_taper=True)
 
 
 def spectral_synthesis_field(RF, shape, res=1.0, *, draws=None):
@@ -326,6 +357,8 @@ class chain:
                                     RF.range_min_y, RF.range_max_y, RF.scale_min, RF.scale_max, RF.nugget_max)
                 ctx.set_blocks(RF.pairs, RF.edge_masks, RF.resolution)
             self._ctx, self._ctx_key = ctx, key
+        if RF is not None:
+            self._ctx.set_generation_method(bool(getattr(RF, "spectral", True)), getattr(RF, "n_modes", 1000))
         return self._ctx
 
     def loss(self, massConvResidual, dataDiff):
@@ -724,7 +757,6 @@ class ChainBatch:
 
     def __init__(self, chain_obj, RF, initial_beds, keys, iter0=1, device=None, track_resampled=False):
         import torch
-        RF._require_spectral()
         self.torch = torch
         shape = tuple(initial_beds.shape)
         if len(shape) != 3 or shape[1:] != chain_obj.xx.shape:

@@ -36,12 +36,14 @@ PROTOTYPES = {
     "gmc_destroy": (C.c_int, [_c_p]),
     "gmc_set_static": (C.c_int, [_c_p] + [_c_p] * 5 + [_c_p, _c_p, _c_p, _i64, _c_p, _f64, _f64]),
     "gmc_set_field_model": (C.c_int, [_c_p, C.c_int, _f64, C.c_int] + [_f64] * 7),
+    "gmc_set_generation_method": (C.c_int, [_c_p, C.c_int, C.c_int]),
     "gmc_set_blocks": (C.c_int, [_c_p, C.c_int, _c_p, _c_p, _c_p, _c_p, _f64]),
     "gmc_residual": (C.c_int, [_c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_residual_loss": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_residual_loss_range": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, C.c_int, _c_p]),
     "gmc_loss": (C.c_int, [_c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_field_spectral": (C.c_int, [_c_p, C.c_int] + [_c_p] * 9 + [_u64, C.c_int, _c_p, _i64, _c_p]),
+    "gmc_field_randmeth": (C.c_int, [_c_p, C.c_int] + [_c_p] * 6 + [C.c_int, _c_p, _c_p, _c_p, _u64, C.c_int, _c_p, _i64, _c_p]),
     "gmc_step_injected": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _i64, _c_p, _c_p, _c_p, C.c_int, C.c_int,
                                     _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_run": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _u64, C.c_int, _c_p, _c_p, _c_p, _i64, _i64, _c_p,
@@ -182,6 +184,10 @@ class Context:
                                            float(range_min_x), float(range_max_x), float(range_min_y),
                                            float(range_max_y), float(scale_min), float(scale_max), float(nugget_max)))
 
+    def set_generation_method(self, spectral, n_modes=1000):
+        """RandField.set_generation_method (MCMC.py:514): False selects the randomization-method proposal (A5)."""
+        check(self.lib.gmc_set_generation_method(self._h, int(bool(spectral)), int(n_modes)))
+
     def set_blocks(self, pairs, edge_masks, field_resolution):
         pairs = np.asarray(pairs)
         n = pairs.shape[1]
@@ -222,6 +228,13 @@ class Context:
         check(self.lib.gmc_field_spectral(self._h, pair.shape[0], _ptr(pair), _ptr(scale), _ptr(nug), _ptr(range_x),
                                           _ptr(range_y), _ptr(z_re), _ptr(z_im), _ptr(z_nug), _ptr(seeds),
                                           int(iteration), int(bool(apply_taper)), _ptr(f_out), f_out.shape[1], _stream()))
+
+    def field_randmeth(self, pair, scale, nug, range_x, range_y, angle_deg, f_out, n_modes=1000, modes=None, z_nug=None,
+                       seeds=None, iteration=0, apply_taper=True):
+        check(self.lib.gmc_field_randmeth(self._h, pair.shape[0], _ptr(pair), _ptr(scale), _ptr(nug), _ptr(range_x),
+                                          _ptr(range_y), _ptr(angle_deg), int(n_modes), _ptr(modes), _ptr(z_nug),
+                                          _ptr(seeds), int(iteration), int(bool(apply_taper)), _ptr(f_out),
+                                          f_out.shape[1], _stream()))
 
     def step_injected(self, bed, mcres, ssq, f, hw, centre, u, hmax, wmax, accepted_out, loss_out, loss_next_out=None,
                       resampled=None):

@@ -132,6 +132,11 @@ struct gmc_ctx {
     int step_smem_bytes;
     int step_tile_off;     // offset (in doubles) of the candidate tile inside the step kernel's dynamic shared memory
     int step_ctas_per_sm;
+    int spectral;          // RandField.set_generation_method: 1 = FFT synthesis (A3), 0 = randomization method (A5)
+    int n_modes;           // wave vectors per randomization-method field (gstools mode_no, default 1000)
+    int rm_smem_bytes;     // dynamic shared memory / tile offset of the randomization-method kernels
+    int rm_tile_off;
+    double field_res;      // grid spacing of the proposal fields (gmc_set_blocks)
     int64_t launches;
     long long* d_phase;    // optional per-phase cycle counters of run_kernel (debug)
     gmc_sgs_state* sgs;    // small-scale (SGS) chain tables, see sgs.cu
@@ -186,7 +191,8 @@ struct Philox {
 };
 
 // Stream ids (counter word 3).  Counter = (draw index, iteration lo, iteration hi, stream).
-enum { GMC_STREAM_RF_SCALARS = 0, GMC_STREAM_NOISE = 1, GMC_STREAM_NUGGET = 2, GMC_STREAM_CHAIN = 3 };
+enum { GMC_STREAM_RF_SCALARS = 0, GMC_STREAM_NOISE = 1, GMC_STREAM_NUGGET = 2, GMC_STREAM_CHAIN = 3,
+       GMC_STREAM_RM_MODE = 8, GMC_STREAM_RM_AMP = 9 };   // 5, 6: small-scale chain (sgs.cu)
 
 // uniform in (0,1), exactly representable: (k + 0.5) * 2^-52 with a 52-bit k
 __device__ __forceinline__ double u01_open(uint32_t hi, uint32_t lo) {

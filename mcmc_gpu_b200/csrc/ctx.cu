@@ -60,6 +60,10 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->step_smem_bytes = 0;
     c->step_tile_off = 0;
     c->step_ctas_per_sm = 0;
+    c->spectral = 1;
+    c->n_modes = 1000;
+    c->rm_smem_bytes = c->rm_tile_off = 0;
+    c->field_res = 0.0;
     c->launches = 0;
     c->d_phase = nullptr;
     c->sgs = nullptr;
@@ -187,6 +191,16 @@ extern "C" int gmc_set_field_model(gmc_ctx* c, int model, double smoothness, int
     return GMC_OK;
 }
 
+// RandField.set_generation_method (MCMC.py:514-522)
+extern "C" int gmc_set_generation_method(gmc_ctx* c, int spectral, int n_modes) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_set_generation_method: ctx is NULL");
+    if (!spectral && (n_modes < 1 || n_modes > (1 << 20)))
+        GMC_FAIL(GMC_EINVAL, "gmc_set_generation_method: n_modes=%d outside [1, 2^20]", n_modes);
+    c->spectral = spectral ? 1 : 0;
+    if (!spectral) c->n_modes = n_modes;
+    return GMC_OK;
+}
+
 // ---- FFT plans -----------------------------------------------------------------------------------------------
 static bool factorize(int n, GmcFftPlan& p) {
     p.n = n;
@@ -220,6 +234,7 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
     if (n_pairs < 1 || !pair_w || !pair_h || !edge_masks || !offsets)
         GMC_FAIL(GMC_EINVAL, "gmc_set_blocks: empty block table or NULL pointer");
     if (!(field_resolution > 0.0)) GMC_FAIL(GMC_EINVAL, "gmc_set_blocks: field_resolution must be > 0");
+    c->field_res = field_resolution;
     GMC_CUDA(cudaSetDevice(c->device));
     std::vector<GmcPair> pairs(n_pairs);
     std::vector<GmcFftPlan> plans;

@@ -840,6 +840,249 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// A5: randomization-method proposal (RandField.get_random_field, MCMC.py:625-687 -> gstools SRF / RandMeth, mode_no
+// wave vectors):  field(p) = sqrt(var / N) * sum_m [ z1_m cos(k_m . p) + z2_m sin(k_m . p) ],  var = 1, p = (x res, y res).
+// On the regular block grid the phase separates, k.p = kx x res + ky y res, so with a = kx x res, b = ky y res
+//   z1 cos(a+b) + z2 sin(a+b) = cos b (z1 cos a + z2 sin a) + sin b (z2 cos a - z1 sin a)
+// and the field is the product of an [h x 2N] table (cos b, sin b) with a [2N x w] table (P, Q): 2 N (h + w) sincos
+// instead of 2 N h w, and a rank-2N update held in registers (5 x 5 outputs per thread, 16 x 16 threads).
+// The wave vectors are isotropic-frame samples k' = r (cos phi, sin phi): phi uniform, r by inversion of the model's
+// radial spectral distribution in two dimensions (gstools model definitions, rescale factors included):
+//   Gaussian     rho = exp(-(pi/4)(d/l)^2)                        r = sqrt(pi)/l * sqrt(-ln(1-u))
+//   Exponential  rho = exp(-d/l)                                  r = sqrt(1/(1-u)^2 - 1) / l
+//   Matern       rho = 2^(1-nu)/Gamma(nu) (sqrt(nu) d/l)^nu K_nu   r = sqrt(nu ((1-u)^(-1/nu) - 1)) / l
+// mapped to the grid frame by the model's rotation and anisotropy: k = R(theta) diag(1, l1/l2) k'.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RM_CHUNK = 16;                 // modes per shared-memory table chunk
+constexpr int RM_EDGE = 80;                  // rows / columns of one register-tile pass
+constexpr int RM_T = RM_EDGE / 16;           // outputs per thread per axis
+static_assert(GMC_STEP_THREADS == 256, "the randomization-method register tiling assumes 16 x 16 threads");
+
+struct RandMethParams {
+    int model, n_modes;
+    double nu, len, inv_anis, cos_t, sin_t;
+};
+
+__device__ __forceinline__ RandMethParams make_randmeth(const GmcFieldModel& fm, int n_modes, double range_x, double range_y,
+                                                        double angle_deg) {
+    RandMethParams rp;
+    rp.model = fm.model;
+    rp.n_modes = n_modes;
+    rp.nu = fm.smoothness;
+    // len_scale = [range1, range2] / sqrt(3) | / 3 | / 2 (MCMC.py:657-676); main length l1, anisotropy ratio l2 / l1
+    const double dv = (fm.model == GMC_GAUSSIAN) ? sqrt(3.0) : (fm.model == GMC_EXPONENTIAL ? 3.0 : 2.0);
+    const double l1 = div_rn(range_x, dv), l2 = div_rn(range_y, dv);
+    rp.len = l1;
+    rp.inv_anis = div_rn(l1, l2);
+    sincos(div_rn(mul_rn(angle_deg, 3.141592653589793), 180.0), &rp.sin_t, &rp.cos_t);   // angles = angle*np.pi/180
+    return rp;
+}
+
+// mode m of the step: out = (kx, ky, z1, z2), wave vector in rad per length unit of `res`
+__device__ __noinline__ void rm_mode(const RandMethParams& rp, const Philox& rng, uint32_t m, uint32_t it_lo, uint32_t it_hi,
+                                     double* out) {
+    const uint4 a = rng(m, it_lo, it_hi, GMC_STREAM_RM_MODE);
+    const double u = u01_open(a.x, a.y);
+    double s, c;
+    sincospi(2.0 * u01_open(a.z, a.w), &s, &c);
+    double r;
+    if (rp.model == GMC_GAUSSIAN) r = sqrt(-log1p(-u)) * 1.7724538509055159 / rp.len;
+    else if (rp.model == GMC_EXPONENTIAL) r = sqrt(u * (2.0 - u)) / (1.0 - u) / rp.len;
+    else r = sqrt(rp.nu * expm1(-log1p(-u) / rp.nu)) / rp.len;
+    const double k0 = r * c, k1 = r * s * rp.inv_anis;
+    out[0] = rp.cos_t * k0 - rp.sin_t * k1;
+    out[1] = rp.sin_t * k0 + rp.cos_t * k1;
+    box_muller(rng(m, it_lo, it_hi, GMC_STREAM_RM_AMP), out[2], out[3]);
+}
+
+// Synthesises the field (times `scale`) into buf as F[y * w + x]; the tables live at buf + tab_off (4 RM_CHUNK RM_EDGE
+// doubles, past the largest field).  Nugget noise (times scale, as the reference scales the whole gstools field) and
+// taper are applied by the consumer through the returned view.
+template <bool INJECT>
+__device__ FieldView synth_randmeth(const GmcDev& d, double* buf, int tab_off, const GmcPair& pr, double res, double scale,
+                                    double nug, const RandMethParams& rp, const Philox& rng, uint32_t it_lo, uint32_t it_hi,
+                                    const double* __restrict__ modes_inj, const double* __restrict__ z_nug, bool apply_taper) {
+    __shared__ double s_mode[RM_CHUNK][4];
+    const int h = pr.h, w = pr.w;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double* A = buf + tab_off;                    // [2 RM_CHUNK][RM_EDGE]: cos b, sin b
+    double* B = A + 2 * RM_CHUNK * RM_EDGE;       // [2 RM_CHUNK][RM_EDGE]: P, Q
+    const double amp = scale * sqrt(1.0 / (double)rp.n_modes);
+    for (int py = 0; py < h; py += RM_EDGE)
+        for (int px = 0; px < w; px += RM_EDGE) {
+            const int hp = min(RM_EDGE, h - py), wp = min(RM_EDGE, w - px);
+            const FastDiv dline(hp + wp);
+            double acc[RM_T][RM_T];
+#pragma unroll
+            for (int i = 0; i < RM_T; ++i)
+#pragma unroll
+                for (int j = 0; j < RM_T; ++j) acc[i][j] = 0.0;
+            for (int m0 = 0; m0 < rp.n_modes; m0 += RM_CHUNK) {
+                if (threadIdx.x < RM_CHUNK) {
+                    const int m = m0 + threadIdx.x;
+                    double v[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (m < rp.n_modes) {
+                        if (INJECT) {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) v[q] = modes_inj[4 * m + q];
+                        } else rm_mode(rp, rng, (uint32_t)m, it_lo, it_hi, v);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) s_mode[threadIdx.x][q] = v[q];
+                }
+                __syncthreads();
+                for (int e = threadIdx.x; e < RM_CHUNK * (hp + wp); e += GMC_STEP_THREADS) {
+                    const int mm = dline.div(e), p = e - mm * (hp + wp);
+                    double sn, cs;
+                    if (p < hp) {
+                        sincos(s_mode[mm][1] * ((double)(py + p) * res), &sn, &cs);
+                        A[(2 * mm) * RM_EDGE + p] = cs;
+                        A[(2 * mm + 1) * RM_EDGE + p] = sn;
+                    } else {
+                        const int x = p - hp;
+                        sincos(s_mode[mm][0] * ((double)(px + x) * res), &sn, &cs);
+                        const double z1 = s_mode[mm][2], z2 = s_mode[mm][3];
+                        B[(2 * mm) * RM_EDGE + x] = z1 * cs + z2 * sn;
+                        B[(2 * mm + 1) * RM_EDGE + x] = z2 * cs - z1 * sn;
+                    }
+                }
+                __syncthreads();
+#pragma unroll 2
+                for (int k = 0; k < 2 * RM_CHUNK; ++k) {
+                    double a[RM_T], b[RM_T];
+#pragma unroll
+                    for (int i = 0; i < RM_T; ++i) a[i] = A[k * RM_EDGE + ty + 16 * i];
+#pragma unroll
+                    for (int j = 0; j < RM_T; ++j) b[j] = B[k * RM_EDGE + tx + 16 * j];
+#pragma unroll
+                    for (int i = 0; i < RM_T; ++i)
+#pragma unroll
+                        for (int j = 0; j < RM_T; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                }
+            }
+            // rows / columns past (hp, wp) multiplied stale table entries: never stored
+#pragma unroll
+            for (int i = 0; i < RM_T; ++i)
+#pragma unroll
+                for (int j = 0; j < RM_T; ++j) {
+                    const int y = ty + 16 * i, x = tx + 16 * j;
+                    if (y < hp && x < wp) buf[(py + y) * w + (px + x)] = amp * acc[i][j];
+                }
+        }
+    __syncthreads();
+    FieldView fv;
+    fv.F = buf;
+    fv.fpitch = w;
+    fv.w = w;
+    fv.sq_nug = (nug > 0.0) ? sqrt(nug) * scale : 0.0;
+    fv.taper = apply_taper ? d.edge_masks + pr.mask_off : nullptr;
+    fv.z_nug = z_nug;
+    return fv;
+}
+
+template <bool INJECT>
+__global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
+    field_randmeth_kernel(GmcDev d, int n_modes, double res, int tab_off, const int32_t* __restrict__ pair,
+                          const double* __restrict__ scale, const double* __restrict__ nug, const double* __restrict__ range_x,
+                          const double* __restrict__ range_y, const double* __restrict__ angle_deg,
+                          const double* __restrict__ modes, const double* __restrict__ z_nug,
+                          const uint64_t* __restrict__ seeds, uint64_t iter, int apply_taper, double* __restrict__ f_out,
+                          int64_t stride) {
+    __shared__ GmcPair s_pair;
+    double* buf = reinterpret_cast<double*>(gmc_smem);
+    const int i = blockIdx.x;
+    if (threadIdx.x == 0) s_pair = d.pairs[pair[i]];
+    __syncthreads();
+    const Philox rng(INJECT ? 0ull : seeds[i]);
+    const uint32_t it_lo = (uint32_t)iter, it_hi = (uint32_t)(iter >> 32);
+    const RandMethParams rp = make_randmeth(d.fm, n_modes, range_x[i], range_y[i], angle_deg[i]);
+    const FieldView fv = synth_randmeth<INJECT>(d, buf, tab_off, s_pair, res, scale[i], nug[i], rp, rng, it_lo, it_hi,
+                                                INJECT ? modes + (int64_t)i * n_modes * 4 : nullptr,
+                                                INJECT ? z_nug + i * stride : nullptr, apply_taper != 0);
+    const int h = s_pair.h, w = s_pair.w;
+    for (int e = threadIdx.x; e < h * w; e += GMC_STEP_THREADS) {
+        double f = field_value<INJECT>(fv, e / w, e % w, rng, it_lo, it_hi);
+        if (fv.taper) f = mul_rn(f, __ldg(fv.taper + e));                               // MCMC.py:778
+        f_out[i * stride + e] = f;
+    }
+}
+
+// chain_crf.run with the randomization-method proposal: same step as run_kernel, other field source.  The field costs
+// ~100x the FFT synthesis (as in the reference), so the block's HBM traffic is simply staged after it.
+__global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
+    run_randmeth_kernel(GmcDev d, int n_modes, double res, int tab_off, double* bed_all, double* mcres_all, double* ssq_all,
+                        const uint64_t* __restrict__ seeds, uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache,
+                        int32_t* blocks_cache, int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all,
+                        int resync_every, int tile_off) {
+    __shared__ double scratch[40];
+    __shared__ StepScalars sc;
+    __shared__ GmcPair s_pair;
+    __shared__ RandMethParams s_rp;
+    double* buf = reinterpret_cast<double*>(gmc_smem);
+    const int c = blockIdx.x;
+    const int64_t plane = (int64_t)d.H * d.W;
+    double* bed = bed_all + c * plane;
+    double* mcres = mcres_all + c * plane;
+    int32_t* resampled = resampled_all ? resampled_all + c * plane : nullptr;
+    const Philox rng(seeds[c]);
+    double ssq = ssq_all[c];
+    PhaseClock pc;
+    pc.acc = nullptr;
+
+    for (int k = 0; k < n_steps; ++k) {
+        const uint64_t it = iter0 + (uint64_t)k;
+        const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
+        if (resync_every > 0 && it % (uint64_t)resync_every == 0) ssq = resync_ssq(d, mcres, scratch);
+        if (threadIdx.x == 0) {
+            const GmcFieldModel& fm = d.fm;
+            const uint4 r0 = rng(0u, it_lo, it_hi, GMC_STREAM_RF_SCALARS), r1 = rng(1u, it_lo, it_hi, GMC_STREAM_RF_SCALARS);
+            const uint4 r2 = rng(2u, it_lo, it_hi, GMC_STREAM_RF_SCALARS);
+            const uint4 c0 = rng(0u, it_lo, it_hi, GMC_STREAM_CHAIN), c1 = rng(1u, it_lo, it_hi, GMC_STREAM_CHAIN);
+            // RandField stream: block size, scale, nugget, range(s), angle                MCMC.py:755, 642-653
+            sc.pair = (int)bounded_u64(r0.x, r0.y, (uint64_t)d.n_pairs);
+            sc.scale = div_rn(add_rn(fm.scale_min, mul_rn(sub_rn(fm.scale_max, fm.scale_min), u01_halfopen(r0.z, r0.w))), 3.0);
+            sc.nug = add_rn(0.0, mul_rn(fm.nugget_max, u01_halfopen(r1.x, r1.y)));
+            sc.range_x = add_rn(fm.range_min_x, mul_rn(sub_rn(fm.range_max_x, fm.range_min_x), u01_halfopen(r1.z, r1.w)));
+            double angle = 0.0;
+            if (fm.isotropic) sc.range_y = sc.range_x;
+            else {
+                sc.range_y = add_rn(fm.range_min_y, mul_rn(sub_rn(fm.range_max_y, fm.range_min_y), u01_halfopen(r2.x, r2.y)));
+                angle = mul_rn(180.0, u01_halfopen(r2.z, r2.w));
+            }
+            // chain stream: identical to run_kernel                                        MCMC.py:1253-1261, 1336
+            if (d.n_centre_cells > 0) {
+                const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
+                sc.ix = cell / d.W;
+                sc.iy = cell - sc.ix * d.W;
+            } else {
+                sc.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
+                sc.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
+            }
+            sc.u = u01_halfopen(c1.x, c1.y);
+            s_pair = d.pairs[sc.pair];
+            sc.h = s_pair.h;
+            sc.w = s_pair.w;
+            block_window(sc, d.H, d.W);
+            s_rp = make_randmeth(fm, n_modes, sc.range_x, sc.range_y, angle);
+        }
+        __syncthreads();
+        const FieldView fv = synth_randmeth<false>(d, buf, tab_off, s_pair, res, sc.scale, sc.nug, s_rp, rng, it_lo, it_hi,
+                                                   nullptr, nullptr, true);
+        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off);
+        step_tail<false>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
+                         nullptr, pc);
+        if (threadIdx.x == 0) {
+            const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
+            if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
+            if (step_cache) step_cache[slot] = (uint8_t)sc.accept;
+            if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(sc.ix, sc.iy, sc.h, sc.w);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ssq_all[c] = ssq;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host entry points
 // ---------------------------------------------------------------------------------------------------------------
 static size_t tile_bytes(int h, int w) { return (size_t)(h + 2) * (w + 2) * sizeof(double); }
@@ -864,6 +1107,17 @@ int gmc_step_configure(gmc_ctx* c) {
     GMC_CUDA(cudaFuncSetAttribute(field_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     c->step_smem_bytes = (int)need;
     c->step_tile_off = (int)(fmax / sizeof(double));
+    // randomization method: field [h][w] at 0 (<= fmax), mode tables share the tile region (the tile is staged after them)
+    const size_t rm_tab = (size_t)4 * RM_CHUNK * RM_EDGE * sizeof(double);
+    const size_t rm_need = fmax + std::max((tmax + 15) & ~(size_t)15, rm_tab);
+    c->rm_smem_bytes = 0;
+    if (rm_need <= prop.sharedMemPerBlockOptin) {
+        GMC_CUDA(cudaFuncSetAttribute(run_randmeth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rm_need));
+        GMC_CUDA(cudaFuncSetAttribute(field_randmeth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rm_need));
+        GMC_CUDA(cudaFuncSetAttribute(field_randmeth_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rm_need));
+        c->rm_smem_bytes = (int)rm_need;
+        c->rm_tile_off = c->step_tile_off;
+    }
     int nb = 0;
     GMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, run_kernel, GMC_STEP_THREADS, need));
     c->step_ctas_per_sm = nb;
@@ -898,6 +1152,31 @@ extern "C" int gmc_field_spectral(gmc_ctx* c, int n, const int32_t* pair, const 
         field_kernel<true><<<n, GMC_STEP_THREADS, c->step_smem_bytes, st>>>(c->dev, pair, scale, nug, range_x, range_y, z_re, z_im, z_nug, seeds, iter, apply_taper, f_out, stride);
     else
         field_kernel<false><<<n, GMC_STEP_THREADS, c->step_smem_bytes, st>>>(c->dev, pair, scale, nug, range_x, range_y, z_re, z_im, z_nug, seeds, iter, apply_taper, f_out, stride);
+    c->launches++;
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+extern "C" int gmc_field_randmeth(gmc_ctx* c, int n, const int32_t* pair, const double* scale, const double* nug,
+                                  const double* range_x, const double* range_y, const double* angle_deg, int n_modes,
+                                  const double* modes, const double* z_nug, const uint64_t* seeds, uint64_t iter,
+                                  int apply_taper, double* f_out, int64_t stride, void* stream) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_field_randmeth: ctx is NULL");
+    if (!c->have_blocks || !c->have_model) GMC_FAIL(GMC_ESTATE, "gmc_field_randmeth: call gmc_set_field_model and gmc_set_blocks first");
+    if (n < 1) GMC_FAIL(GMC_EINVAL, "gmc_field_randmeth: n must be >= 1");
+    if (n_modes < 1 || n_modes > (1 << 20)) GMC_FAIL(GMC_EINVAL, "gmc_field_randmeth: n_modes=%d outside [1, 2^20]", n_modes);
+    if (!pair || !scale || !nug || !range_x || !range_y || !angle_deg || !f_out) GMC_FAIL(GMC_EINVAL, "gmc_field_randmeth: NULL argument");
+    if (stride < (int64_t)c->max_h * c->max_w) GMC_FAIL(GMC_ESHAPE, "gmc_field_randmeth: stride %lld < max block %d", (long long)stride, c->max_h * c->max_w);
+    const bool inject = modes || z_nug;
+    if (inject && !(modes && z_nug)) GMC_FAIL(GMC_EINVAL, "gmc_field_randmeth: modes and z_nug must be both given or both NULL");
+    if (!inject && !seeds) GMC_FAIL(GMC_EINVAL, "gmc_field_randmeth: seeds required when no modes are injected");
+    if (!c->rm_smem_bytes) GMC_FAIL(GMC_EUNSUPPORTED, "gmc_field_randmeth: the block table needs more shared memory than the device offers");
+    GMC_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (inject)
+        field_randmeth_kernel<true><<<n, GMC_STEP_THREADS, c->rm_smem_bytes, st>>>(c->dev, n_modes, c->field_res, c->rm_tile_off, pair, scale, nug, range_x, range_y, angle_deg, modes, z_nug, seeds, iter, apply_taper, f_out, stride);
+    else
+        field_randmeth_kernel<false><<<n, GMC_STEP_THREADS, c->rm_smem_bytes, st>>>(c->dev, n_modes, c->field_res, c->rm_tile_off, pair, scale, nug, range_x, range_y, angle_deg, modes, z_nug, seeds, iter, apply_taper, f_out, stride);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;
@@ -938,6 +1217,15 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
         GMC_FAIL(GMC_ESHAPE, "gmc_run: cache window [%lld, %lld) exceeds stride %lld", (long long)cache_offset,
                  (long long)(cache_offset + n_steps), (long long)cache_stride);
     if (n_steps == 0) return GMC_OK;
+    if (!c->spectral) {                      // RandField.set_generation_method(False): A5 proposal
+        if (!c->rm_smem_bytes) GMC_FAIL(GMC_EUNSUPPORTED, "gmc_run: the block table needs more shared memory than the device offers");
+        run_randmeth_kernel<<<C, GMC_STEP_THREADS, c->rm_smem_bytes, (cudaStream_t)stream>>>(
+            c->dev, c->n_modes, c->field_res, c->rm_tile_off, bed, mcres, ssq, seeds, iter0, n_steps, loss_cache, step_cache,
+            blocks_cache, cache_stride, cache_offset, resampled, resync_every, c->rm_tile_off);
+        c->launches++;
+        GMC_CUDA(cudaGetLastError());
+        return GMC_OK;
+    }
     run_kernel<<<C, GMC_STEP_THREADS, c->step_smem_bytes, (cudaStream_t)stream>>>(c->dev, bed, mcres, ssq, seeds, iter0, n_steps,
                                                                                  loss_cache, step_cache, blocks_cache,
                                                                                  cache_stride, cache_offset, resampled,

@@ -8,6 +8,7 @@ import numpy as np
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = 0x9E3779B9, 0xBB67AE85
 STREAM_RF_SCALARS, STREAM_NOISE, STREAM_NUGGET, STREAM_CHAIN = 0, 1, 2, 3
+STREAM_RM_MODE, STREAM_RM_AMP = 8, 9
 _M32 = np.uint64(0xFFFFFFFF)
 
 
@@ -87,8 +88,21 @@ def hermitian_noise(key, it, h, w):
     return A, B
 
 
-def step_draws(key, it, n_pairs, pairs, fm, H, W, centre_cells):
-    """All random inputs of iteration `it` of one chain, in oracle terms."""
+def randmeth_modes(key, it, n_modes, model, range_x, range_y, angle_deg, nu):
+    """(kx, ky, z1, z2) of the randomization-method field of iteration `it` (step.cu rm_mode): the radius quantile and
+    direction come from one Philox block of stream RM_MODE, the two amplitudes from one block of stream RM_AMP."""
+    from oracle import randmeth_oracle as R
+    lo, hi = it & 0xFFFFFFFF, (it >> 32) & 0xFFFFFFFF
+    m = np.arange(n_modes, dtype=np.uint32)
+    a = philox4x32(key, m, lo, hi, STREAM_RM_MODE)
+    kx, ky = R.grid_wave_vectors(model, u01_open(a[0], a[1]), u01_open(a[2], a[3]), range_x, range_y, angle_deg, nu)
+    z1, z2 = box_muller(philox4x32(key, m, lo, hi, STREAM_RM_AMP))
+    return kx, ky, z1, z2
+
+
+def step_draws(key, it, n_pairs, pairs, fm, H, W, centre_cells, randmeth=False):
+    """All random inputs of iteration `it` of one chain, in oracle terms.  randmeth: the proposal is the
+    randomization-method field (anisotropy angle drawn, no spectral noise planes)."""
     lo, hi = it & 0xFFFFFFFF, (it >> 32) & 0xFFFFFFFF
     r0 = [int(x) for x in philox4x32(key, 0, lo, hi, STREAM_RF_SCALARS)]
     r1 = [int(x) for x in philox4x32(key, 1, lo, hi, STREAM_RF_SCALARS)]
@@ -98,14 +112,19 @@ def step_draws(key, it, n_pairs, pairs, fm, H, W, centre_cells):
     scale = (f64(fm["scale_min"]) + (f64(fm["scale_max"]) - f64(fm["scale_min"])) * u(r0[2], r0[3])) / 3.0
     nug = 0.0 + f64(fm["nugget_max"]) * u(r1[0], r1[1])
     range_x = f64(fm["range_min_x"]) + (f64(fm["range_max_x"]) - f64(fm["range_min_x"])) * u(r1[2], r1[3])
+    angle = 0.0
     if fm["isotropic"]:
         range_y = range_x
     else:
         r2 = [int(x) for x in philox4x32(key, 2, lo, hi, STREAM_RF_SCALARS)]
         range_y = f64(fm["range_min_y"]) + (f64(fm["range_max_y"]) - f64(fm["range_min_y"])) * u(r2[0], r2[1])
+        angle = 180.0 * u(r2[2], r2[3])
     bw, bh = int(pairs[0, pick]), int(pairs[1, pick])
     e = np.arange(bh * bw, dtype=np.uint32)
-    z_re, z_im = hermitian_noise(key, it, bh, bw)
+    if randmeth:
+        z_re = z_im = np.zeros(bh * bw)
+    else:
+        z_re, z_im = hermitian_noise(key, it, bh, bw)
     z_nug, _ = box_muller(philox4x32(key, e, lo, hi, STREAM_NUGGET))
     c0 = [int(x) for x in philox4x32(key, 0, lo, hi, STREAM_CHAIN)]
     c1 = [int(x) for x in philox4x32(key, 1, lo, hi, STREAM_CHAIN)]
@@ -114,6 +133,6 @@ def step_draws(key, it, n_pairs, pairs, fm, H, W, centre_cells):
         ix, iy = divmod(cell, W)
     else:
         ix, iy = bounded(c0[0], c0[1], H), bounded(c0[2], c0[3], W)
-    return dict(pair=pick, scale=float(scale), nug=float(nug), range_x=float(range_x), range_y=float(range_y),
+    return dict(pair=pick, scale=float(scale), nug=float(nug), range_x=float(range_x), range_y=float(range_y), angle=float(angle),
                 z_re=z_re.reshape(bh, bw), z_im=z_im.reshape(bh, bw), z_nug=z_nug.reshape(bh, bw), idx_x=ix, idx_y=iy,
                 u=u(c1[0], c1[1]))
