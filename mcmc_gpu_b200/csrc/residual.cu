@@ -18,6 +18,8 @@
 //     flight per warp): bytes in flight, not registers or warps, are what HBM latency has to be covered with;
 //   * x/(2 res) uses the precomputed reciprocal with one FMA residual correction (correctly rounded, see div_const).
 #include "common.cuh"
+#include <cmath>
+#include <cstdlib>
 
 #ifndef RS_RW
 #define RS_RW 2                       // rows per warp (even)
@@ -42,7 +44,6 @@ struct ResSmem {
     double vely[RS_TH + 2][RS_PITCH];
     double dhdt[RS_TH][RS_PITCH];
     double smb[RS_TH][RS_PITCH];
-    uint8_t mc[RS_TH][RS_TW];
     double ring[RS_STAGES][RS_WARPS][RS_RW + 2][RS_PITCH];   // per-warp landing zone of the streamed bed rows
 };
 
@@ -99,7 +100,6 @@ struct LaneStatics {
 };
 
 __device__ __forceinline__ void load_statics(const ResSmem& S, const LaneGeom& g, LaneStatics& L) {
-    L.mcbits = 0;
 #pragma unroll
     for (int k = 0; k < RS_RW + 2; ++k) {
         L.sf[k] = *reinterpret_cast<const double2*>(&S.surf[g.wr0 + k][g.sc]);
@@ -112,9 +112,22 @@ __device__ __forceinline__ void load_statics(const ResSmem& S, const LaneGeom& g
         L.sm[k] = *reinterpret_cast<const double2*>(&S.smb[g.wr0 + k][g.sc]);
         L.hsf[k] = S.surf[g.wr0 + k + 1][g.hsc];
         L.hvx[k] = S.velx[g.wr0 + k][g.hsc];
-        const uchar2 m = *reinterpret_cast<const uchar2*>(&S.mc[g.wr0 + k][2 * g.lane]);
-        L.mcbits |= (m.x ? 1u : 0u) << (2 * k) | (m.y ? 1u : 0u) << (2 * k + 1);
     }
+}
+
+// loss-mask bits of the lane's cells, straight from global memory (issued before the staging wait, used after it)
+__device__ __forceinline__ unsigned load_mask_bits(const GmcDev& d, const LaneGeom& g, int c0) {
+    unsigned bits = 0;
+#pragma unroll
+    for (int k = 0; k < RS_RW; ++k) {
+        const int i = g.i0 + k;
+        if (i < g.H && g.v0) {
+            const uint8_t* f = d.flags + (int64_t)i * g.W + c0;
+            if (__ldg(f) & FLAG_MC) bits |= 1u << (2 * k);
+            if (g.v1 && (__ldg(f + 1) & FLAG_MC)) bits |= 1u << (2 * k + 1);
+        }
+    }
+    return bits;
 }
 
 // true when |x| lies in [2^-930, 2^930]: the FMA-corrected quotient is then free of over/underflow (see div_const)
@@ -236,18 +249,22 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics&
 template <bool WRITE_RES, bool DO_LOSS, bool VEC, bool INTERIOR>
 __device__ __forceinline__ void chain_loop(const GmcDev& d, ResSmem& S, const LaneGeom& g, int warp, const double* __restrict__ pb,
                                            double* __restrict__ po, double* __restrict__ pp, int64_t plane, int n_tiles, int C,
-                                           double r_res, double r_two_res) {
+                                           double r_res, double r_two_res, unsigned mcbits) {
     const int G = gridDim.z;
     const int64_t cstride = (int64_t)G * plane, pstride = (int64_t)G * n_tiles;
     const int n_iter = (C - (int)blockIdx.z + G - 1) / G;          // chains blockIdx.z, +G, +2G, ...
-    LaneStatics L;
-    load_statics(S, g, L);
-    // prologue: RS_STAGES-1 chains in flight (empty groups keep the group count uniform)
+    // prologue: RS_STAGES-1 chains in flight (empty groups keep the group count uniform), issued behind the statics'
+    // copy group so that both latencies overlap
 #pragma unroll
     for (int s = 0; s < RS_STAGES - 1; ++s) {
         if (s < n_iter) fetch_bed<VEC, INTERIOR>(g, pb + s * cstride, S.ring[s][warp]);
         cp_async_commit();
     }
+    cp_async_wait<RS_STAGES - 1>();                                // this thread's share of the statics has landed
+    __syncthreads();                                               // ... and everybody else's
+    LaneStatics L;
+    load_statics(S, g, L);
+    L.mcbits = mcbits;
     int stage = 0;
     for (int it = 0; it < n_iter; ++it) {
         const int nxt = it + RS_STAGES - 1;
@@ -275,23 +292,36 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
     const int tx0 = blockIdx.x * RS_TW, ty0 = blockIdx.y * RS_TH;
     const int64_t plane = (int64_t)H * W;
 
-    // ---- stage the chain-independent fields of this tile (+ one-cell halo) --------------------------------
+    // ---- stage the chain-independent fields of this tile (+ one-cell halo): asynchronous copies, all in flight at once
+    // (one exposed memory latency per CTA instead of one per loop trip); cells outside the grid read as 0.
+    const bool cta_interior = tx0 > 0 && tx0 + RS_TW < W && ty0 > 0 && ty0 + RS_TH < H;
     for (int t = tid; t < (RS_TH + 2) * (RS_TW + 2); t += RS_THREADS) {
         const int rr = t / (RS_TW + 2), cc = t - rr * (RS_TW + 2);      // rr in [0,18): row ty0-1+rr; cc in [0,66): col tx0-1+cc
         const int i = ty0 - 1 + rr, j = tx0 - 1 + cc;
-        const bool in = i >= 0 && i < H && j >= 0 && j < W;
+        const bool in = cta_interior || (i >= 0 && i < H && j >= 0 && j < W);
         const int64_t idx = (int64_t)i * W + j;
-        S.surf[rr][cc + 1] = in ? __ldg(d.surf + idx) : 0.0;
-        S.vely[rr][cc + 1] = in ? __ldg(d.vely + idx) : 0.0;
-        if (rr >= 1 && rr <= RS_TH) {
-            S.velx[rr - 1][cc + 1] = in ? __ldg(d.velx + idx) : 0.0;
-            S.dhdt[rr - 1][cc + 1] = in ? __ldg(d.dhdt + idx) : 0.0;
-            S.smb[rr - 1][cc + 1] = in ? __ldg(d.smb + idx) : 0.0;
-            if (cc >= 1 && cc <= RS_TW) S.mc[rr - 1][cc - 1] = in ? (__ldg(d.flags + idx) & FLAG_MC) : 0;
+        const bool mid = rr >= 1 && rr <= RS_TH;
+        if (in) {
+            cp_async8(&S.surf[rr][cc + 1], d.surf + idx);
+            cp_async8(&S.vely[rr][cc + 1], d.vely + idx);
+            if (mid) {
+                cp_async8(&S.velx[rr - 1][cc + 1], d.velx + idx);
+                cp_async8(&S.dhdt[rr - 1][cc + 1], d.dhdt + idx);
+                cp_async8(&S.smb[rr - 1][cc + 1], d.smb + idx);
+            }
+        } else {
+            S.surf[rr][cc + 1] = 0.0;
+            S.vely[rr][cc + 1] = 0.0;
+            if (mid) S.velx[rr - 1][cc + 1] = S.dhdt[rr - 1][cc + 1] = S.smb[rr - 1][cc + 1] = 0.0;
         }
     }
-    for (int t = tid; t < RS_STAGES * RS_WARPS * (RS_RW + 2) * RS_PITCH; t += RS_THREADS) (&S.ring[0][0][0][0])[t] = 0.0;
-    __syncthreads();
+    cp_async_commit();
+    if (!cta_interior) {
+        // boundary tiles: padding lanes / rows of the ring are read but never copied; give them a defined value.  Must
+        // precede the first ring copy.
+        for (int t = tid; t < RS_STAGES * RS_WARPS * (RS_RW + 2) * RS_PITCH; t += RS_THREADS) (&S.ring[0][0][0][0])[t] = 0.0;
+        __syncthreads();
+    }
 
     LaneGeom g;
     g.W = W;
@@ -299,7 +329,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
     g.lane = lane;
     g.wr0 = warp * RS_RW;                         // first tile row of this warp
     g.i0 = ty0 + g.wr0;                           // first grid row
-    if (g.i0 >= H) return;                        // warp-uniform; no block-wide barriers below
+    const bool warp_on = g.i0 < H && (int)blockIdx.z < C;      // warp-uniform; idle warps still join the staging barrier
     const int c0 = tx0 + 2 * lane;                // first grid column of this lane
     g.sc = 2 * lane + 2;                          // smem column of c0 (16 B aligned)
     g.v0 = c0 < W;
@@ -324,9 +354,14 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
     double* po = WRITE_RES ? res_all + (int64_t)blockIdx.z * plane + lane_off : nullptr;
     double* pp = partials + (int64_t)blockIdx.z * n_tiles + tile_id;
     const bool interior = tx0 > 0 && tx0 + RS_TW < W && g.i0 > 0 && g.i0 + RS_RW < H;   // warp-uniform
-    if ((int)blockIdx.z >= C) return;
-    if (interior) chain_loop<WRITE_RES, DO_LOSS, VEC, true>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res);
-    else chain_loop<WRITE_RES, DO_LOSS, VEC, false>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res);
+    const unsigned mcbits = (DO_LOSS && warp_on) ? load_mask_bits(d, g, c0) : 0u;
+    if (!warp_on) {
+        cp_async_wait<0>();
+        __syncthreads();
+        return;
+    }
+    if (interior) chain_loop<WRITE_RES, DO_LOSS, VEC, true>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res, mcbits);
+    else chain_loop<WRITE_RES, DO_LOSS, VEC, false>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res, mcbits);
 }
 
 // masked nansum of squares of given residuals: one CTA per (chunk, chain)
@@ -417,9 +452,21 @@ static int launch_residual(gmc_ctx* c, const double* bed, double* res_out, doubl
     // different streams
     double* partials = c->d_partials + (size_t)chain0 * c->n_tiles;
     const int tx = tiles_x(c), ty = tiles_y(c);
-    // chain groups: enough CTAs for ~8 per SM, but keep >= 8 chains per CTA to amortise the staged statics
-    int groups = (24 * c->sm_count + tx * ty - 1) / (tx * ty);     // ~6 waves of 4 CTAs/SM: small tail
-    groups = std::max(1, std::min(groups, std::max(1, C / 8)));
+    // chain groups G (gridDim.z): a CTA keeps its tile's statics in registers and walks C/G chains.  Few groups amortise
+    // the tile prologue (~4 chain-iterations' worth) over many chains; the CTA count tiles*G should fill whole waves of
+    // RS_MIN_CTAS CTAs per SM.  Pick the G that maximises (useful fraction of a CTA) x (wave efficiency).
+    const int slots = RS_MIN_CTAS * c->sm_count;
+    int groups = 1;
+    double best = -1.0;
+    for (int G = 1; G <= std::max(1, std::min(C / 4, 256)); ++G) {
+        const double n = (double)C / G, waves = (double)tx * ty * G / slots;
+        const double score = n / (n + 4.0) * (waves / std::ceil(waves)) * (waves < 1.0 ? waves : 1.0);
+        if (score > best + 1e-9) {
+            best = score;
+            groups = G;
+        }
+    }
+    if (const char* e = getenv("GMC_RS_GROUPS")) groups = std::max(1, std::min(atoi(e), C));   // tuning override
     groups = std::min(groups, 65535);
     const dim3 grid(tx, ty, groups);
     // 16-byte accesses need even W and 16 B aligned bases
