@@ -62,19 +62,24 @@ struct LaneGeom {
     int W, H, i0, lane, wr0, sc, hsc;
     unsigned rowmask;      // bit k: grid row i0-1+k exists
     bool v0, v1, hval;
+    bool own;              // this lane's columns belong to this tile (false for the overlap of the shifted last tile)
     bool xl_edge, xr0_edge, xr1_edge;
     int k_top, k_bot;      // k of grid row 0 / H-1 inside this warp's rows, or -1
     int64_t hoff;          // offset of the halo column relative to the lane's first column
 };
 
-// INTERIOR: the warp's rows and all 64 columns (+halo) lie strictly inside the grid: no predicates, no edge rules.
+// MODE 1 (interior): the warp's rows and all 64 columns (+halo) lie strictly inside the grid: no predicates, no edge
+// rules.  MODE 2 (column edge): rows strictly inside, all 64 columns valid, but the tile touches the first or last grid
+// column (tiles are 64 wide everywhere: the last one is shifted left to end at W, see the kernel) - only lane 0 / lane
+// 31 need np.gradient's one-sided rule.  MODE 0: everything else (first/last rows, odd or narrow grids), fully predicated.
 // Every lane copies exactly the cells it will read back itself, so cp.async.wait_group alone orders the ring.
-template <bool VEC, bool INTERIOR>
+template <bool VEC, int MODE>
 __device__ __forceinline__ void fetch_bed(const LaneGeom& g, const double* __restrict__ p, double (*slot)[RS_PITCH]) {
+    constexpr bool INTERIOR = MODE == 1, ROWS_IN = MODE != 0;
     // p -> (row i0-1, column c0) of the chain's bed; slot -> this warp's [RS_RW+2][RS_PITCH] ring stage
 #pragma unroll
     for (int k = 0; k < RS_RW + 2; ++k) {
-        if (INTERIOR || (((g.rowmask >> k) & 1u) && g.v0)) {
+        if (ROWS_IN || (((g.rowmask >> k) & 1u) && g.v0)) {
             const double* q = p + (int64_t)k * g.W;
             if (VEC) cp_async16(&slot[k][g.sc], q);
             else {
@@ -86,7 +91,7 @@ __device__ __forceinline__ void fetch_bed(const LaneGeom& g, const double* __res
     if (INTERIOR ? (g.lane == 0 || g.lane == 31) : g.hval) {
 #pragma unroll
         for (int k = 1; k <= RS_RW; ++k)
-            if (INTERIOR || ((g.rowmask >> k) & 1u)) cp_async8(&slot[k][g.hsc], p + (int64_t)k * g.W + g.hoff);
+            if (ROWS_IN || ((g.rowmask >> k) & 1u)) cp_async8(&slot[k][g.hsc], p + (int64_t)k * g.W + g.hoff);
     }
 }
 
@@ -133,10 +138,11 @@ __device__ __forceinline__ unsigned load_mask_bits(const GmcDev& d, const LaneGe
 // true when |x| lies in [2^-930, 2^930]: the FMA-corrected quotient is then free of over/underflow (see div_const)
 __device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
 
-template <bool WRITE_RES, bool DO_LOSS, bool VEC, bool INTERIOR>
+template <bool WRITE_RES, bool DO_LOSS, bool VEC, int MODE>
 __device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics& L, const LaneGeom& g,
                                              const double (*bed)[RS_PITCH], double* __restrict__ out,
                                              double* __restrict__ partial, double r_res, double r_two_res) {
+    constexpr bool INTERIOR = MODE == 1, ROWS_IN = MODE != 0;
     // ---- fluxes: fy for rows -1..RS_RW, fx for rows 0..RS_RW-1 --------------------------------------------------
     double fy0[RS_RW + 2], fy1[RS_RW + 2], fx0[RS_RW], fx1[RS_RW], fxh[RS_RW];
 #pragma unroll
@@ -155,7 +161,7 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics&
     }
     // np.gradient's one-sided first/last rows as data: duplicating the edge row into the missing neighbour turns the
     // central difference into (f[1]-f[0]) resp. (f[n-1]-f[n-2]); only the divisor changes (res instead of 2 res).
-    if (!INTERIOR) {
+    if (!ROWS_IN) {
 #pragma unroll
         for (int k = 0; k < RS_RW; ++k) {
             if (k == g.k_top) { fy0[k] = fy0[k + 1]; fy1[k] = fy1[k + 1]; }
@@ -186,9 +192,9 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics&
             if (!INTERIOR) {
                 if (g.xl_edge) l = fx0[k];                        // column 0:   (f[1]   - f[0]  )/res
                 if (g.xr1_edge) rr = fx1[k];                      // column W-1: (f[W-1] - f[W-2])/res (second column)
-                if (g.xr0_edge) a0 = fx0[k];                      // column W-1 as first column (odd W)
-                if ((k == g.k_top) || (k == g.k_bot)) { deny = d.res; rdeny = r_res; }
-                if (g.xl_edge || g.xr0_edge) { den0 = d.res; rden0 = r_res; }
+                if (!ROWS_IN && g.xr0_edge) a0 = fx0[k];          // column W-1 as first column (odd W)
+                if (!ROWS_IN && ((k == g.k_top) || (k == g.k_bot))) { deny = d.res; rdeny = r_res; }
+                if (g.xl_edge || (!ROWS_IN && g.xr0_edge)) { den0 = d.res; rden0 = r_res; }
                 if (g.xr1_edge) { den1 = d.res; rden1 = r_res; }
             }
             num[u][0] = sub_rn(a0, l);
@@ -207,16 +213,18 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics&
                 quo[u][j] = copysign(fma(fma(-den[u][j], q, num[u][j]), rdn[u][j], q), q);
                 int e = hi_abs(q);
                 if ((e | __double2loint(q)) == 0) e = 0x3ff00000;            // exact zero: the fast path is exact
-                if (!INTERIOR && !(((g.rowmask >> (k + 1)) & 1u) && g.v0)) e = 0x3ff00000;   // padding lane/row: ignored
+                if (!ROWS_IN && !(((g.rowmask >> (k + 1)) & 1u) && g.v0)) e = 0x3ff00000;   // padding lane/row: ignored
                 lo = min(lo, e);
                 hi = max(hi, e);
             }
         }
-        if (lo < 0x05d00000 || hi > 0x7a100000) {                 // zero, subnormal, huge, inf or nan somewhere: exact path
+        if (lo < 0x05d00000 || hi > 0x7a100000) {                 // zero, subnormal, huge, inf or nan somewhere (cold)
 #pragma unroll
             for (int u = 0; u < 2; ++u)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) quo[u][j] = div_slow(num[u][j], den[u][j]);
+                for (int j = 0; j < 4; ++j) {
+                    quo[u][j] = div_slow(num[u][j], den[u][j]);
+                }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -224,18 +232,18 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics&
             const double2 dh = L.dh[k], sm = L.sm[k];
             const double r0 = sub_rn(add_rn(add_rn(quo[u][0], quo[u][2]), dh.x), sm.x);
             const double r1 = sub_rn(add_rn(add_rn(quo[u][1], quo[u][3]), dh.y), sm.y);
-            if (INTERIOR || (((g.rowmask >> (k + 1)) & 1u) && g.v0)) {
-                if (WRITE_RES) {
+            if (ROWS_IN || (((g.rowmask >> (k + 1)) & 1u) && g.v0)) {
+                if (WRITE_RES && (INTERIOR || g.own)) {
                     double* q = out + (int64_t)(k + 1) * g.W;
                     if (VEC) __stcs(reinterpret_cast<double2*>(q), make_double2(r0, r1));
                     else {
                         __stcs(q, r0);
-                        if (INTERIOR || g.v1) __stcs(q + 1, r1);
+                        if (ROWS_IN || g.v1) __stcs(q + 1, r1);
                     }
                 }
-                if (DO_LOSS) {
+                if (DO_LOSS) {                                   // mask bits of columns another tile owns are already 0
                     if (((L.mcbits >> (2 * k)) & 1u) && r0 == r0) acc = add_rn(acc, mul_rn(r0, r0));
-                    if ((INTERIOR || g.v1) && ((L.mcbits >> (2 * k + 1)) & 1u) && r1 == r1) acc = add_rn(acc, mul_rn(r1, r1));
+                    if ((ROWS_IN || g.v1) && ((L.mcbits >> (2 * k + 1)) & 1u) && r1 == r1) acc = add_rn(acc, mul_rn(r1, r1));
                 }
             }
         }
@@ -246,7 +254,7 @@ __device__ __forceinline__ void compute_rows(const GmcDev& d, const LaneStatics&
     }
 }
 
-template <bool WRITE_RES, bool DO_LOSS, bool VEC, bool INTERIOR>
+template <bool WRITE_RES, bool DO_LOSS, bool VEC, int MODE>
 __device__ __forceinline__ void chain_loop(const GmcDev& d, ResSmem& S, const LaneGeom& g, int warp, const double* __restrict__ pb,
                                            double* __restrict__ po, double* __restrict__ pp, int64_t plane, int n_tiles, int C,
                                            double r_res, double r_two_res, unsigned mcbits) {
@@ -257,7 +265,7 @@ __device__ __forceinline__ void chain_loop(const GmcDev& d, ResSmem& S, const La
     // copy group so that both latencies overlap
 #pragma unroll
     for (int s = 0; s < RS_STAGES - 1; ++s) {
-        if (s < n_iter) fetch_bed<VEC, INTERIOR>(g, pb + s * cstride, S.ring[s][warp]);
+        if (s < n_iter) fetch_bed<VEC, MODE>(g, pb + s * cstride, S.ring[s][warp]);
         cp_async_commit();
     }
     cp_async_wait<RS_STAGES - 1>();                                // this thread's share of the statics has landed
@@ -270,10 +278,10 @@ __device__ __forceinline__ void chain_loop(const GmcDev& d, ResSmem& S, const La
         const int nxt = it + RS_STAGES - 1;
         int ns = stage + RS_STAGES - 1;
         if (ns >= RS_STAGES) ns -= RS_STAGES;
-        if (nxt < n_iter) fetch_bed<VEC, INTERIOR>(g, pb + (int64_t)nxt * cstride, S.ring[ns][warp]);
+        if (nxt < n_iter) fetch_bed<VEC, MODE>(g, pb + (int64_t)nxt * cstride, S.ring[ns][warp]);
         cp_async_commit();
         cp_async_wait<RS_STAGES - 1>();                            // this lane's copies of chain `it` have landed
-        compute_rows<WRITE_RES, DO_LOSS, VEC, INTERIOR>(d, L, g, S.ring[stage][warp], po, pp, r_res, r_two_res);
+        compute_rows<WRITE_RES, DO_LOSS, VEC, MODE>(d, L, g, S.ring[stage][warp], po, pp, r_res, r_two_res);
         if (WRITE_RES) po += cstride;
         pp += pstride;
         if (++stage == RS_STAGES) stage = 0;
@@ -288,8 +296,18 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
     extern __shared__ __align__(16) unsigned char rs_raw[];
     ResSmem& S = *reinterpret_cast<ResSmem*>(rs_raw);
     const int H = d.H, W = d.W;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx0 = blockIdx.x * RS_TW, ty0 = blockIdx.y * RS_TH;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    // read once through a volatile asm: otherwise the compiler re-reads SR_TID.X inside the chain loop to save a register,
+    // and the S2R latency (~25 cycles, twice per trip) lands on the critical path
+    int lane;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+    // Tiles are RS_TW wide; with 16-byte accesses (even W >= RS_TW) the last tile of a row is shifted left to end exactly
+    // at W, so every lane of every tile holds valid columns.  The columns it shares with its left neighbour are computed
+    // twice (same bits) but stored and summed once (`own`).
+    const bool shift = VEC && W >= RS_TW;
+    const int tx_nom = blockIdx.x * RS_TW;
+    const int tx0 = shift ? min(tx_nom, W - RS_TW) : tx_nom;
+    const int ty0 = blockIdx.y * RS_TH;
     const int64_t plane = (int64_t)H * W;
 
     // ---- stage the chain-independent fields of this tile (+ one-cell halo): asynchronous copies, all in flight at once
@@ -334,6 +352,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
     g.sc = 2 * lane + 2;                          // smem column of c0 (16 B aligned)
     g.v0 = c0 < W;
     g.v1 = c0 + 1 < W;
+    g.own = c0 >= tx_nom;
     const int hcol = (lane == 0) ? c0 - 1 : c0 + 2;          // lane 0: left of the tile, lane 31: right of it
     g.hval = (lane == 0 && hcol >= 0) || (lane == 31 && hcol < W);
     g.hsc = (lane == 0) ? g.sc - 1 : g.sc + 2;
@@ -354,14 +373,16 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
     double* po = WRITE_RES ? res_all + (int64_t)blockIdx.z * plane + lane_off : nullptr;
     double* pp = partials + (int64_t)blockIdx.z * n_tiles + tile_id;
     const bool interior = tx0 > 0 && tx0 + RS_TW < W && g.i0 > 0 && g.i0 + RS_RW < H;   // warp-uniform
-    const unsigned mcbits = (DO_LOSS && warp_on) ? load_mask_bits(d, g, c0) : 0u;
+    const unsigned mcbits = (DO_LOSS && warp_on && g.own) ? load_mask_bits(d, g, c0) : 0u;
     if (!warp_on) {
         cp_async_wait<0>();
         __syncthreads();
         return;
     }
-    if (interior) chain_loop<WRITE_RES, DO_LOSS, VEC, true>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res, mcbits);
-    else chain_loop<WRITE_RES, DO_LOSS, VEC, false>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res, mcbits);
+    const bool rows_in = g.i0 > 0 && g.i0 + RS_RW < H;                                  // warp-uniform
+    if (interior) chain_loop<WRITE_RES, DO_LOSS, VEC, 1>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res, mcbits);
+    else if (shift && rows_in) chain_loop<WRITE_RES, DO_LOSS, VEC, 2>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res, mcbits);
+    else chain_loop<WRITE_RES, DO_LOSS, VEC, 0>(d, S, g, warp, pb, po, pp, plane, n_tiles, C, r_res, r_two_res, mcbits);
 }
 
 // masked nansum of squares of given residuals: one CTA per (chunk, chain)
