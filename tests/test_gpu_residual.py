@@ -43,7 +43,8 @@ def test_topography_tensor_api():
     assert same_values(res.cpu().numpy(), gold["residual"])
 
 
-@pytest.mark.parametrize("H,W,C", [(2, 2, 1), (2, 9, 3), (33, 2, 2), (37, 53, 4), (64, 128, 2), (200, 200, 3), (131, 257, 5)])
+@pytest.mark.parametrize("H,W,C", [(2, 2, 1), (2, 9, 3), (33, 2, 2), (37, 53, 4), (64, 128, 2), (200, 200, 3), (131, 257, 5),
+                                   (70, 64, 2), (45, 100, 3), (40, 500, 2), (19, 66, 9)])
 def test_batched_residual_and_loss(H, W, C):
     import torch
     from mcmc_gpu_b200._lib import Context
@@ -72,6 +73,38 @@ def test_batched_residual_and_loss(H, W, C):
         tol = 1e-12 * max(abs(ref_loss), 1e-300)
         assert abs(loss_fused[c] - ref_loss) <= tol and abs(loss_sep[c] - ref_loss) <= tol
     assert np.allclose(ssq_d.cpu().numpy() / (2 * sigma ** 2), loss_fused, rtol=1e-15)
+
+
+def test_signed_zero_and_special_quotients_are_bit_identical():
+    """Zero thickness makes every flux +-0, so every quotient is +-0 (sign from the velocities); with dhdt = -0 the
+    sign survives into the residual.  Also huge / tiny / infinite fluxes, which leave the fast division path."""
+    import torch
+    from gpu_helpers import bits_equal
+    from mcmc_gpu_b200._lib import Context
+    H, W = 40, 200
+    g = np.random.default_rng(5)
+    surf = 1000.0 + g.standard_normal((H, W))
+    velx, vely = g.standard_normal((H, W)), g.standard_normal((H, W))
+    dhdt, smb = np.full((H, W), -0.0), np.zeros((H, W))
+    beds = np.stack([surf.copy(), surf - 1.0, surf.copy()])
+    beds[2, 10:20, 50:90] -= 1e300           # huge thickness -> huge fluxes, inf differences
+    beds[2, 25:30, 100:140] -= 1e-310        # below the spacing of surf: thickness still exactly 0
+    velx2 = velx.copy()
+    velx2[5, 5], velx2[6, 100] = np.inf, 1e-320
+    for vx in (velx, velx2):
+        ctx = Context(H, W, 3)
+        ctx.set_static(surf, vx, vely, dhdt, smb, np.ones((H, W)), np.ones((H, W)), None, None, 500.0, 1.0)
+        bed_d = torch.as_tensor(beds).cuda()
+        res_d = torch.empty_like(bed_d)
+        ctx.residual(bed_d, res_d)
+        res = res_d.cpu().numpy()
+        with np.errstate(all="ignore"):
+            for c in range(3):
+                ref = O.mass_conservation_residual(beds[c], surf, vx, vely, dhdt, smb, 500.0)
+                nan = np.isnan(ref)
+                assert np.array_equal(np.isnan(res[c]), nan)
+                assert bits_equal(np.where(nan, 0.0, res[c]), np.where(nan, 0.0, ref)), c
+        assert np.signbit(res[0]).any() and (~np.signbit(res[0])).any()
 
 
 def test_chain_loss_method_matches_golden():
