@@ -217,6 +217,11 @@ GMC_API int gmc_allreduce_moments(gmc_ctx* ctx, void* nccl_comm, double* sum, do
 GMC_API int gmc_min_dist(int device, const double* px, const double* py, int64_t M, const double* qx, const double* qy,
                          int64_t N, double* out, void* stream);
 
+/* PIL ImageFilter.ModeFilter(size) as Topography.get_highvel_boundary applies it to the binary region mask
+ * (Topography.py:551-553): in/out dev [H][W] u8 with values 0 / 255 (any non-zero input counts as 255); window
+ * (2*(size/2)+1)^2 clipped to the image, majority wins, 0 on ties. */
+GMC_API int gmc_mode_filter_binary(int device, const uint8_t* in, uint8_t* out, int H, int W, int size, void* stream);
+
 /* ---- introspection for tests and bench ---------------------------------------------------------------------- */
 
 /* Number of kernel launches issued through this context since creation. */

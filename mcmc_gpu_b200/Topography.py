@@ -58,3 +58,33 @@ def get_mass_conservation_residual(bed, surf, velx, vely, dhdt, smb, resolution)
 def get_mass_conservation_residual_tensor(bed, surf, velx, vely, dhdt, smb, resolution):
     """torch.Tensor in, CUDA float64 torch.Tensor out (reference Topography.py:602-612 is float32 torch.gradient)."""
     return _residual(bed, (surf, velx, vely, dhdt, smb), float(resolution))
+
+
+def get_highvel_boundary(velx, vely, velmag_threshold, grounded_ice_mask, ocean_mask, distance_max, xx, yy, smooth_mode=10):
+    """High-velocity update region (reference Topography.py:546-571): grounded cells at least `velmag_threshold` fast,
+    plus ocean, smoothed by a `smooth_mode` mode filter, then grown by `distance_max` inside the grounded mask.
+
+    The reference runs PIL's ModeFilter and an O(N^2) Python double loop for the nearest-region distance; here both are
+    kernels (`mode_filter_kernel`, `min_dist_kernel`).  The distance is the same correctly rounded expression
+    sqrt((y-y')^2 + (x-x')^2) minimised over the region, so the returned mask equals the reference's exactly.
+    """
+    import torch
+    from . import _lib
+    from .Utilities import min_dist_from_mask
+    velx, vely = np.asarray(velx, dtype=np.float64), np.asarray(vely, dtype=np.float64)
+    grounded = np.asarray(grounded_ice_mask)
+    mask = (grounded.astype(bool)) & (np.sqrt(velx ** 2 + vely ** 2) >= velmag_threshold)
+    mask = mask | np.asarray(ocean_mask).astype(bool)
+    dev = _lib.require_cuda()
+    lib = _lib.load()
+    H, W = mask.shape
+    img = torch.as_tensor((mask * 255).astype(np.uint8)).to(dev)
+    out = torch.empty_like(img)
+    _lib.check(lib.gmc_mode_filter_binary(dev.index, img.data_ptr(), out.data_ptr(), H, W, int(smooth_mode),
+                                          torch.cuda.current_stream().cuda_stream))
+    mask_mat = (out.cpu().numpy() // 255).astype(int)
+    hard = (mask_mat == 1) & (grounded == 1)
+    if not hard.any():                       # the reference's nanmin over an all-NaN map is NaN: nothing is "close"
+        return np.zeros(mask.shape, dtype=grounded.dtype) & grounded
+    mask_dist = min_dist_from_mask(np.asarray(xx, dtype=np.float64), np.asarray(yy, dtype=np.float64), hard)
+    return (mask_dist < distance_max) & grounded

@@ -127,3 +127,35 @@ extern "C" int gmc_min_dist(int device, const double* px, const double* py, int6
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;
 }
+
+// ---- setup helper: the mode filter of Topography.get_highvel_boundary --------------------------------
+// The reference smooths the binary region mask with PIL's ImageFilter.ModeFilter(size) (Topography.py:551-553).  PIL's
+// rule (ModeFilter.c): histogram of the (2*(size/2)+1)^2 window clipped to the image, most frequent value wins, the lower
+// value on ties, and the pixel is kept when no value occurs more than twice.  For the binary {0, 255} image the reference
+// builds, the histogram is one count.  One thread per pixel; the image is a few hundred KB and stays in L2.
+__global__ void __launch_bounds__(256)
+    mode_filter_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int H, int W, int r) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const int y0 = max(0, y - r), y1 = min(H - 1, y + r), x0 = max(0, x - r), x1 = min(W - 1, x + r);
+    int c1 = 0;
+    for (int yy = y0; yy <= y1; ++yy) {
+        const uint8_t* row = in + (int64_t)yy * W;
+        for (int xx = x0; xx <= x1; ++xx) c1 += (row[xx] != 0);
+    }
+    const int n = (y1 - y0 + 1) * (x1 - x0 + 1), c0 = n - c1;
+    uint8_t v = in[(int64_t)y * W + x];
+    if (max(c0, c1) > 2) v = (c1 > c0) ? 255 : 0;
+    out[(int64_t)y * W + x] = v;
+}
+
+extern "C" int gmc_mode_filter_binary(int device, const uint8_t* in, uint8_t* out, int H, int W, int size, void* stream) {
+    if (!in || !out) GMC_FAIL(GMC_EINVAL, "gmc_mode_filter_binary: NULL argument");
+    if (H < 1 || W < 1 || size < 1) GMC_FAIL(GMC_EINVAL, "gmc_mode_filter_binary: H, W and size must be >= 1");
+    if (in == out) GMC_FAIL(GMC_EINVAL, "gmc_mode_filter_binary: in-place filtering is not supported");
+    GMC_CUDA(cudaSetDevice(device));
+    const dim3 grid((W + 31) / 32, (H + 7) / 8);
+    mode_filter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in, out, H, W, size / 2);
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}

@@ -35,7 +35,7 @@ def quiet(fn, *a, **k):
 # ---- the named trajectory cases: shared with tests/cases.py so oracle and reference see the same inputs ----
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from cases import (TRAJECTORY_CASES, FIELD_CASES, SGS_CASES, residual_case_inputs, build_case_grids,   # noqa: E402
-                   build_sgs_inputs)
+                   build_sgs_inputs, highvel_case_inputs)
 
 
 def reference_chain(case):
@@ -95,6 +95,13 @@ def main():
         out = reference_sgs_chain(case)
         np.savez_compressed(os.path.join(OUT, f"sgs_{name}.npz"), **out)
         print(f"sgs_{name}: final loss {out['loss'][-1]!r}, acceptance {out['steps'].mean():.3f}")
+
+    # (5) region-mask preprocessing: Topography.get_highvel_boundary (the O(N^2) double loop, so a small grid)
+    hb = highvel_case_inputs()
+    out = Topography.get_highvel_boundary(hb["velx"], hb["vely"], hb["threshold"], hb["grounded"], hb["ocean"], hb["distance_max"],
+                                          hb["xx"], hb["yy"], smooth_mode=hb["smooth_mode"])
+    np.savez_compressed(os.path.join(OUT, "highvel_boundary.npz"), mask_final=out)
+    print("highvel_boundary:", out.shape, out.dtype, int(out.sum()), "cells")
 
     # (1) residual + loss known answers
     ri = residual_case_inputs()

@@ -76,6 +76,25 @@ def residual_case_inputs() -> dict:
                 resolution=res, sigma_mc=2.5)
 
 
+def highvel_case_inputs() -> dict:
+    """44x57 grid: a fast ice stream with a noisy edge, a floating/ocean corner, speckle that the mode filter removes."""
+    H, W = 44, 57
+    g = np.random.default_rng(77)
+    res = 500.0
+    xx, yy = np.meshgrid(np.arange(W) * res, np.arange(H) * res)
+    stream = 120.0 * np.exp(-((yy - 9e3 - 0.15 * xx) / 4e3) ** 2)
+    velx = stream * 0.9 + 8.0 * g.standard_normal((H, W))
+    vely = stream * 0.3 + 8.0 * g.standard_normal((H, W))
+    velx[g.random((H, W)) < 0.03] = 300.0                    # isolated fast pixels
+    grounded = np.ones((H, W), dtype=np.int64)
+    grounded[30:, 40:] = 0                                   # floating ice / ocean
+    grounded[3:6, 3:5] = 0                                   # an ungrounded hole inside the sheet
+    ocean = (1 - grounded).astype(np.int64)
+    ocean[3:6, 3:5] = 0
+    return dict(xx=xx, yy=yy, velx=velx, vely=vely, threshold=50.0, grounded=grounded, ocean=ocean, distance_max=2200.0,
+                smooth_mode=10)
+
+
 # ---- small-scale SGS chain cases (chain_sgs.run, MCMC.py:1599) ------------------------------------------------------
 SGS_CASES = {
     # tutorial-like: detrended + normal-score transformed bed, Matern variogram, ordinary kriging with octant search
