@@ -119,11 +119,15 @@ def test_device_normals_match_numpy_emulation_and_are_standard():
     assert abs(z.mean()) < 4 / np.sqrt(z.size) and abs(z.var() - 1) < 6 * np.sqrt(2 / z.size)
 
 
-def test_unsupported_generation_method_is_loud():
+def test_bad_generation_method_arguments_are_loud():
+    """set_generation_method(False) selects the randomization method (tests/test_gpu_randmeth.py); nonsense mode counts
+    are rejected by the library instead of being clamped."""
     from mcmc_gpu_b200 import MCMC, synthetic as syn
     rf = quiet(MCMC.RandField, 1e3, 2e3, 1e3, 2e3, 1, 2, 0, "Gaussian", True)
     rf.set_block_sizes(10, 12, 10, 12, steps=2)
     rf.set_weight_param(*syn.LOGISTIC, 1e3, 100.0)
-    rf.set_generation_method(False)
-    with pytest.raises(NotImplementedError):
+    rf.set_generation_method(False, n_modes=0)
+    with pytest.raises(ValueError):
         rf.get_rfblock()
+    rf.set_generation_method(False, n_modes=8)
+    assert rf.get_rfblock().shape in {(10, 10), (10, 12), (12, 10), (12, 12)}
