@@ -17,6 +17,7 @@
 // Where the reference calls np.linalg.lstsq (SVD, minimum norm) we solve exactly; the systems are well conditioned
 // (cond ~1e4, |d est| <= 6e-13), parity is <= 1e-9 as for every floating-point result of this chain.
 #include "common.cuh"
+#include <cstdlib>
 
 #define SGS_THREADS 256
 #define SGS_MAX_BLOCK 32          // largest block edge (cells)
@@ -44,6 +45,7 @@ struct SgsDev {
 struct gmc_sgs_state {
     SgsDev dev;
     bool ready;
+    bool warp_solver;
     void* owned[8];
 };
 
@@ -128,6 +130,10 @@ struct SgsShared {
     int oct_n[8];
     int path[SGS_MAX_BLOCK * SGS_MAX_BLOCK];
     short2 near_off[8][SGS_NEAR];                      // the nearest offsets of every octant (almost every search ends here)
+    int16_t ord[SGS_MAX_BLOCK * SGS_MAX_BLOCK];        // warp solver: -1 = radar-conditioned, else position among the nodes to simulate
+    int16_t todo[SGS_MAX_BLOCK * SGS_MAX_BLOCK];       // warp solver: the nodes to simulate, in path order
+    int16_t todo_k[SGS_MAX_BLOCK * SGS_MAX_BLOCK];     // ... and their positions in the full path (index of the injected normals)
+    int n_todo;
     double scratch[40];
     int ix, iy, bsx, bsy, x0, x1, y0, y1, accept, n_nb, err;
     double u;
@@ -137,7 +143,204 @@ __device__ __forceinline__ double lut_cov(const SgsDev& s, int di, int dj) {
     return __ldg(s.lut + (di + 2 * s.hw) * s.lut_w + (dj + 2 * s.hw));
 }
 
+// ---- warp-per-node kriging ------------------------------------------------------------------------------------------
+// Which cells are conditioned when a node's turn comes is known from the path alone (radar cells, cells outside the block,
+// and block cells earlier in the path); the simulated VALUES enter only through est = mean + sum_i w_i (v_i - mean).  So the
+// neighbour search and the kriging solve of every node are independent of each other: eight warps work on eight
+// consecutive path nodes at once (phase 1), then one warp turns the eight (weights, variance) into values in path order
+// (phase 2, a 48-term dot product each).  A warp holds its augmented matrix [Sigma | rho | 1] (48 x 50) in REGISTERS,
+// lane (lr, lc) of a 4 x 8 layout owning rows lr+4a (a<12) and columns lc+8b (b<7) - cyclic, so the shrinking active part
+// stays balanced; per pivot only the pivot row and column pass through a per-warp shared-memory buffer (__syncwarp, no
+// CTA barrier).  Gauss-Jordan without pivoting on the SPD block, as in the CTA-wide solver it replaces for num_points <= 48.
+#define SGS_WN 48
+struct SgsWarpRec {
+    double nval[SGS_WN], w[SGS_WN], rho[SGS_WN];
+    double xrow[2][56], xcol[2][SGS_WN];
+    double dg[SGS_WN], ra[SGS_WN], rb[SGS_WN];
+    int16_t ndi[SGS_WN], ndj[SGS_WN], nsrc[SGS_WN];
+    int n, node, kpath;
+    double var, zn;
+};
+static_assert(8 * sizeof(SgsWarpRec) <= SGS_MAX_NEIGH * SGS_SIG_PITCH * sizeof(double), "warp records must fit in SgsShared::sig");
+
 template <bool INJECT>
+__device__ __forceinline__ void sgs_warp_node(const GmcDev& d, const SgsDev& s, const SgsShared& S, SgsWarpRec& R,
+                                              const double* __restrict__ z, int t_ord, int bw, const double* zn_in,
+                                              const Philox& rng, uint32_t it_lo, uint32_t it_hi) {
+    const int H = d.H, W = d.W, lane = threadIdx.x & 31;
+    const int x0 = S.x0, x1 = S.x1, y0 = S.y0, y1 = S.y1;
+    const int node = S.todo[t_ord];
+    const int bi = node / bw, bj = node - bi * bw;
+    const int i = x0 + bi, j = y0 + bj;
+    // (a) octant search, octants in the reference's order                                       neighbors.py:52-60
+    int n = 0;
+    for (int o = 0; o < 8; ++o) {
+        const int16_t* off = s.oct_off + (int64_t)o * s.lmax * 2;
+        const int cnt = __ldg(s.oct_cnt + o);
+        int found = 0;
+        for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
+            const int t = base + lane;
+            bool ok = false;
+            int di = 0, dj = 0, src = -1;
+            double v = 0.0;
+            if (t < cnt) {
+                if (t < SGS_NEAR) {
+                    const short2 o2 = S.near_off[o][t];
+                    di = o2.x;
+                    dj = o2.y;
+                } else {
+                    di = off[2 * t];
+                    dj = off[2 * t + 1];
+                }
+                const int ci = i + di, cj = j + dj;
+                if (ci >= 0 && ci < H && cj >= 0 && cj < W) {
+                    if (ci >= x0 && ci < x1 && cj >= y0 && cj < y1) {
+                        src = (ci - x0) * bw + (cj - y0);
+                        ok = S.ord[src] < t_ord;                 // radar cell (-1) or simulated earlier in the path
+                    } else {
+                        v = __ldcg(z + (int64_t)ci * W + cj);
+                        ok = (v == v);
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int rank = found + __popc(m & ((1u << lane) - 1u));
+            if (ok && rank < s.per_oct) {
+                const int slot = n + rank;
+                R.ndi[slot] = (int16_t)di;
+                R.ndj[slot] = (int16_t)dj;
+                R.nsrc[slot] = (int16_t)src;
+                R.nval[slot] = v;
+            }
+            found += __popc(m);
+        }
+        n += min(found, s.per_oct);
+    }
+    if (lane == 0) {
+        R.n = n;
+        R.node = node;
+        R.kpath = S.todo_k[t_ord];
+        double zn, z1;
+        if (INJECT) zn = zn_in[S.todo_k[t_ord]];
+        else box_muller(rng((uint32_t)node, it_lo, it_hi, 6u), zn, z1);               // stream 6: node normals
+        R.zn = zn;
+    }
+    __syncwarp();
+    if (n == 0) return;                                      // reported by phase 2 (the reference would widen the radius)
+    // (b) assemble [Sigma | rho | 1] straight into registers                                       _krige.py:20-33
+    const int lr = lane & 3, lc = lane >> 2;
+    double A[12][7];
+    {
+        int rdi[12], rdj[12], cdi[6], cdj[6];
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+            const int r = lr + 4 * a;
+            rdi[a] = (r < n) ? R.ndi[r] : 0;
+            rdj[a] = (r < n) ? R.ndj[r] : 0;
+        }
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const int c = lc + 8 * b;
+            cdi[b] = (c < n) ? R.ndi[c] : 0;
+            cdj[b] = (c < n) ? R.ndj[c] : 0;
+        }
+#pragma unroll
+        for (int a = 0; a < 12; ++a) {
+            const int r = lr + 4 * a;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                const int c = lc + 8 * b;
+                A[a][b] = (r < n && c < n) ? lut_cov(s, rdi[a] - cdi[b], rdj[a] - cdj[b]) : 0.0;
+            }
+            double aug = 0.0;                                 // columns 48 (rho) and 49 (ones) live in lanes lc = 0, 1
+            if (r < n) {
+                if (lc == 0) {
+                    aug = lut_cov(s, -rdi[a], -rdj[a]);
+                    R.rho[r] = aug;
+                } else if (lc == 1) aug = 1.0;
+            }
+            A[a][6] = aug;
+        }
+    }
+    // (c) Gauss-Jordan; pivot p = 4 ap + lrp lives in register row ap of the lanes lr == lrp and in register column
+    // bp = ap / 2 of the lanes lc == p % 8
+#pragma unroll
+    for (int ap = 0; ap < 12; ++ap) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int bp = ap / 2;
+        for (int lrp = 0; lrp < 4; ++lrp) {
+            const int p = 4 * ap + lrp;
+            if (p >= n) break;                                // warp-uniform
+            const int buf = lrp & 1;
+            if (lr == lrp) {
+#pragma unroll
+                for (int b = 0; b < 7; ++b)
+                    if (b >= bp) R.xrow[buf][lc + 8 * b] = A[ap][b];
+            }
+            if (lc == (p & 7)) {
+#pragma unroll
+                for (int a = 0; a < 12; ++a) R.xcol[buf][lr + 4 * a] = A[a][bp];
+            }
+            __syncwarp();
+            const double inv = __drcp_rn(R.xrow[buf][p]);
+            double pr[7];
+#pragma unroll
+            for (int b = 0; b < 7; ++b)
+                if (b >= bp) pr[b] = R.xrow[buf][lc + 8 * b];
+#pragma unroll
+            for (int a = 0; a < 12; ++a) {
+                const int r = lr + 4 * a;
+                const double f = (r != p) ? R.xcol[buf][r] * inv : 0.0;
+#pragma unroll
+                for (int b = 0; b < 7; ++b)
+                    if (b >= bp) A[a][b] = fma(-f, pr[b], A[a][b]);
+            }
+        }
+    }
+    // (d) gather the diagonal and the two solved right-hand sides, then weights and variance     _krige.py:36-43
+#pragma unroll
+    for (int a = 0; a < 12; ++a) {
+        const int r = lr + 4 * a;
+#pragma unroll
+        for (int b = 0; b < 6; ++b)
+            if (r == lc + 8 * b && r < n) R.dg[r] = A[a][b];
+        if (r < n) {
+            if (lc == 0) R.ra[r] = A[a][6];
+            if (lc == 1) R.rb[r] = A[a][6];
+        }
+    }
+    __syncwarp();
+    double xa[2] = {0.0, 0.0}, xb[2] = {0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int r = lane + 32 * q;
+        if (r < n) {
+            const double dg = R.dg[r];
+            xa[q] = R.ra[r] / dg;
+            xb[q] = R.rb[r] / dg;
+        }
+    }
+    double s1a = warp_sum(xa[0] + xa[1]), s1b = warp_sum(xb[0] + xb[1]);
+    s1a = __shfl_sync(0xffffffffu, s1a, 0);
+    s1b = __shfl_sync(0xffffffffu, s1b, 0);
+    const double mu = (s1a - 1.0) / s1b;
+    double pv = 0.0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int r = lane + 32 * q;
+        if (r < n) {
+            const double w = xa[q] - mu * xb[q];
+            R.w[r] = w;
+            pv += w * R.rho[r];
+        }
+    }
+    pv = warp_sum(pv);
+    if (lane == 0) R.var = fabs(s.sill - pv);
+    __syncwarp();
+}
+
+template <bool INJECT, bool WS>
 __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, double* bedc, double* z, double* mcres, double& ssq,
                              int& nviol, const int32_t* path_in, const double* zn_in, const Philox& rng, uint32_t it_lo,
                              uint32_t it_hi, int32_t* resampled, double* loss_next_out) {
@@ -191,6 +394,78 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
     __syncthreads();
 
     mark(0);
+    if constexpr (WS) {
+        // (2w) warp-per-node simulation: list the nodes to simulate in path order ...
+        if (wid == 0) {
+            int count = 0;
+            for (int base = 0; base < nblk; base += 32) {
+                const int k = base + lane;
+                int node = 0;
+                bool unc = false;
+                if (k < nblk) {
+                    node = S.path[k];
+                    const double cur = S.blk_z[node];
+                    unc = !(cur == cur);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, unc);
+                if (k < nblk) {
+                    if (unc) {
+                        const int t = count + __popc(m & ((1u << lane) - 1u));
+                        S.todo[t] = (int16_t)node;
+                        S.todo_k[t] = (int16_t)k;
+                        S.ord[node] = (int16_t)t;
+                    } else S.ord[node] = -1;
+                }
+                count += __popc(m);
+            }
+            if (lane == 0) S.n_todo = count;
+        }
+        __syncthreads();
+        const int n_todo = S.n_todo;
+        SgsWarpRec* recs = reinterpret_cast<SgsWarpRec*>(S.sig);
+        for (int t0 = 0; t0 < n_todo; t0 += 8) {
+            // ... phase 1: eight path nodes, one per warp (search + solve; no simulated value is read)
+            if (t0 + wid < n_todo) sgs_warp_node<INJECT>(d, s, S, recs[wid], z, t0 + wid, bw, zn_in, rng, it_lo, it_hi);
+            __syncthreads();
+            mark(4);
+            // ... phase 2: values in path order                                                    MCMC.py:163-169
+            if (wid == 0) {
+                const int nb = min(8, n_todo - t0);
+                for (int q = 0; q < nb; ++q) {
+                    const SgsWarpRec& R = recs[q];
+                    const int n = R.n;
+                    double val = 0.0;
+                    if (n == 0) {
+                        if (lane == 0) S.err = 1;
+                    } else {
+                        double v[2] = {0.0, 0.0}, wv[2] = {0.0, 0.0};
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const int r = lane + 32 * h2;
+                            if (r < n) {
+                                const int src = R.nsrc[r];
+                                v[h2] = (src >= 0) ? S.blk_z[src] : R.nval[r];
+                                wv[h2] = R.w[r];
+                            }
+                        }
+                        double sv = warp_sum(v[0] + v[1]);
+                        sv = __shfl_sync(0xffffffffu, sv, 0);
+                        const double mean = sv / (double)n;
+                        double pe = 0.0;
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2)
+                            if (lane + 32 * h2 < n) pe += wv[h2] * (v[h2] - mean);
+                        pe = warp_sum(pe);
+                        val = (mean + pe) + sqrt(R.var) * R.zn;                          // MCMC.py:168
+                    }
+                    if (lane == 0) S.blk_z[R.node] = val;
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            mark(5);
+        }
+    } else {
     // (2) sequential simulation along the path                                              MCMC.py:130-169
     for (int k = 0; k < nblk; ++k) {
         const int node = S.path[k];
@@ -417,6 +692,7 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
         }
         __syncthreads();
     }
+    }
 
     mark(5);
     // (3) candidate bed of the block = inverse normal score of the simulated values            MCMC.py:1776-1777
@@ -515,6 +791,7 @@ __device__ __forceinline__ void sgs_window(SgsShared& S, int H, int W) {
     S.y1 = min(W, (int)((double)S.iy + (double)S.bsy / 2.0));
 }
 
+template <bool WS>
 __global__ void __launch_bounds__(SGS_THREADS)
     sgs_step_injected_kernel(GmcDev d, SgsDev s, double* bedc_all, double* z_all, double* mcres_all, double* ssq_all,
                              int32_t* nviol_all, const int32_t* __restrict__ centre, const int32_t* __restrict__ bs,
@@ -539,7 +816,7 @@ __global__ void __launch_bounds__(SGS_THREADS)
     double ssq = ssq_all[c];
     int nviol = nviol_all[c];
     const Philox rng(0ull);
-    sgs_one_step<true>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, path + c * path_stride,
+    sgs_one_step<true, WS>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, path + c * path_stride,
                        zn + c * path_stride, rng, 0u, 0u, resampled_all ? resampled_all + c * plane : nullptr,
                        loss_next_out ? loss_next_out + c : nullptr);
     if (threadIdx.x == 0) {
@@ -551,6 +828,7 @@ __global__ void __launch_bounds__(SGS_THREADS)
     }
 }
 
+template <bool WS>
 __global__ void __launch_bounds__(SGS_THREADS)
     sgs_run_kernel(GmcDev d, SgsDev s, double* bedc_all, double* z_all, double* mcres_all, double* ssq_all, int32_t* nviol_all,
                    const uint64_t* __restrict__ seeds, uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache,
@@ -586,7 +864,7 @@ __global__ void __launch_bounds__(SGS_THREADS)
             sgs_window(S, d.H, d.W);
         }
         __syncthreads();
-        sgs_one_step<false>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, nullptr, nullptr,
+        sgs_one_step<false, WS>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, nullptr, nullptr,
                             rng, it_lo, it_hi, resampled_all ? resampled_all + c * plane : nullptr, nullptr);
         if (threadIdx.x == 0) {
             const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
@@ -684,8 +962,13 @@ extern "C" int gmc_sgs_setup(gmc_ctx* c, const double* trend, const double* zcon
     s.bmax_x = block_max_x;
     s.bmin_y = block_min_y;
     s.bmax_y = block_max_y;
-    GMC_CUDA(cudaFuncSetAttribute(sgs_step_injected_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
-    GMC_CUDA(cudaFuncSetAttribute(sgs_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
+    GMC_CUDA(cudaFuncSetAttribute(sgs_step_injected_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
+    GMC_CUDA(cudaFuncSetAttribute(sgs_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
+    GMC_CUDA(cudaFuncSetAttribute(sgs_step_injected_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
+    GMC_CUDA(cudaFuncSetAttribute(sgs_run_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsShared)));
+    // warp-per-node solver for up to 48 neighbours; GMC_SGS_SOLVER=cta forces the CTA-wide solver (A/B timing, tests)
+    const char* force = getenv("GMC_SGS_SOLVER");
+    st->warp_solver = (s.per_oct * 8 <= SGS_WN) && !(force && force[0] == 'c');
     st->ready = true;
     return GMC_OK;
 }
@@ -740,9 +1023,14 @@ extern "C" int gmc_sgs_step_injected(gmc_ctx* c, double* bedc, double* z, double
     if (rc) return rc;
     if (!bedc || !z || !mcres || !ssq || !nviol || !centre || !block_size || !path || !znorm || !u)
         GMC_FAIL(GMC_EINVAL, "gmc_sgs_step_injected: NULL argument");
-    sgs_step_injected_kernel<<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
-        c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, centre, block_size, path, znorm, path_stride, u, accepted_out, loss_out,
-        loss_next_out, resampled, err_flag);
+    if (c->sgs->warp_solver)
+        sgs_step_injected_kernel<true><<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
+            c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, centre, block_size, path, znorm, path_stride, u, accepted_out, loss_out,
+            loss_next_out, resampled, err_flag);
+    else
+        sgs_step_injected_kernel<false><<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
+            c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, centre, block_size, path, znorm, path_stride, u, accepted_out, loss_out,
+            loss_next_out, resampled, err_flag);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;
@@ -759,9 +1047,14 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
         GMC_FAIL(GMC_ESHAPE, "gmc_sgs_run: cache window exceeds stride");
     if (n_steps == 0) return GMC_OK;
     c->sgs->dev.phase = c->d_phase;
-    sgs_run_kernel<<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds,
-                                                                              iter0, n_steps, loss_cache, step_cache, blocks_cache,
-                                                                              cache_stride, cache_offset, resampled, err_flag);
+    if (c->sgs->warp_solver)
+        sgs_run_kernel<true><<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
+            c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
+            cache_offset, resampled, err_flag);
+    else
+        sgs_run_kernel<false><<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
+            c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
+            cache_offset, resampled, err_flag);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;
