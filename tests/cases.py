@@ -107,6 +107,11 @@ SGS_CASES = {
                      vario=dict(vtype="Exponential", range=[4000.0, 2500.0], sill=900.0, nugget=0.0, isotropic=False,
                                 smoothness=None, azimuth=30.0),
                      transform=False, detrend=False, thin=True),
+    # the tutorial's neighbourhood: 48 neighbours (6 per octant), i.e. full 48 x 48 kriging systems
+    "matern_k48": dict(H=64, W=70, n_iter=30, seed=31, sigma_mc=1.5, blocks=(5, 12, 5, 12), neighbors=48, radius=9e3,
+                       vario=dict(vtype="Matern", range=4000.0, sill=1.0, nugget=0.0, isotropic=True, smoothness=1.2259,
+                                  azimuth=None),
+                       transform=True, detrend=True, n_quantiles=500),
 }
 
 

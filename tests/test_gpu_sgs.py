@@ -36,8 +36,12 @@ def test_normal_score_transform_matches_sklearn_restatement():
     assert np.nanmax(np.abs(b - b_ref) / np.maximum(np.abs(b_ref), 1.0)) <= 1e-11
 
 
+@pytest.mark.parametrize("solver", ["warp", "cta"])
 @pytest.mark.parametrize("name", sorted(SGS_CASES))
-def test_replay_matches_oracle_trajectory(name):
+def test_replay_matches_oracle_trajectory(name, solver, monkeypatch):
+    """Both kriging solvers: warp-per-node (num_points <= 48, the default) and the CTA-wide one it falls back to."""
+    if solver == "cta":
+        monkeypatch.setenv("GMC_SGS_SOLVER", "cta")          # read by gmc_sgs_setup
     case = SGS_CASES[name]
     g, su = oracle_sgs_setup(case)
     ora = S.sgs_chain_run(su, g["bed_init"], case["n_iter"], np.random.default_rng(case["seed"]), record=True)
