@@ -199,6 +199,32 @@ GMC_API int gmc_sgs_run(gmc_ctx* ctx, double* bedc, double* z, double* mcres, do
                         uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache,
                         int64_t cache_stride, int64_t cache_offset, int32_t* resampled, int32_t* err_flag, int C, void* stream);
 
+/* ---- whole-grid SGS: the initial beds of the large-scale chains (gstatsim_custom/interpolate.py:92-191) ---------- */
+
+/* QuantileTransformer(output_distribution='normal') transform / inverse_transform from explicit tables (dev [nq]), as
+ * interpolate.sgs applies them to the data, the bounds and the result (utilities.py:21-24, interpolate.py:240-246, 185). */
+GMC_API int gmc_nst_transform(int device, const double* quantiles, const double* references, int n_quantiles, const double* in,
+                      double* out, int64_t n, int inverse, void* stream);
+
+/* Kriging records of n_real realisations (the loop body of interpolate.py:130-163 without the draw), all nodes in parallel:
+ *   ord  dev [n_real][H*W] i32 : -1 at conditioning cells, else the cell's position in the realisation's path
+ *   path dev [n_real][n_path] i32 : row-major cell indices in simulation order (the shuffled `inds`, :125)
+ *   oct_off / oct_cnt / lmax / hw : octant search lists as for gmc_sgs_setup (neighbors.py:52-60);  lut : covariance of
+ *   integer offsets, [(4hw+1)^2];  num_points <= 48
+ *   rec_n [n_real][n_path] i32 (-1: conditioning cell), rec_idx, rec_w [n_real][n_path][48], rec_sd [n_real][n_path]
+ *   err_flag dev i32: bit 0 set if a node found no neighbour within the radius (the reference widens it by 100 km). */
+GMC_API int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, const int32_t* path, int64_t n_path, int n_real,
+                       const int16_t* oct_off, const int32_t* oct_cnt, int lmax, int hw, int num_points, const double* lut,
+                       double sill, int32_t* rec_n, int32_t* rec_idx, double* rec_w, double* rec_sd, int32_t* err_flag,
+                       void* stream);
+
+/* The draws in path order (interpolate.py:166-183): z dev [n_real][H*W] holds the normal-scored data (anything elsewhere)
+ * and receives the simulated normal scores; noise dev [n_real][n_path]: the standard normal of node t (no bounds) or
+ * the uniform of its truncated-normal draw; bound_lo / bound_hi dev [H*W] normal-scored bounds, or both NULL. */
+GMC_API int gmc_sgs_grid_values(int device, int H, int W, double* z, const int32_t* path, int64_t n_path, int n_real,
+                        const int32_t* rec_n, const int32_t* rec_idx, const double* rec_w, const double* rec_sd,
+                        const double* noise, const double* bound_lo, const double* bound_hi, void* stream);
+
 /* ---- ensemble statistics (new) ---------------------------------------------------------------- */
 
 /* Local part of the posterior mean/variance: sum_out[H][W] = sum_c (bed_c - ref), sumsq_out = sum_c (bed_c - ref)^2. */

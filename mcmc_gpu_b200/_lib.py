@@ -57,6 +57,10 @@ PROTOTYPES = {
     "gmc_sgs_step_injected": (C.c_int, [_c_p] * 10 + [_i64] + [_c_p] * 6 + [C.c_int, _c_p]),
     "gmc_sgs_run": (C.c_int, [_c_p] * 7 + [_u64, C.c_int, _c_p, _c_p, _c_p, _i64, _i64, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_min_dist": (C.c_int, [C.c_int, _c_p, _c_p, _i64, _c_p, _c_p, _i64, _c_p, _c_p]),
+    "gmc_nst_transform": (C.c_int, [C.c_int, _c_p, _c_p, C.c_int, _c_p, _c_p, _i64, C.c_int, _c_p]),
+    "gmc_sgs_grid_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, _c_p, _c_p, _i64, C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int,
+                                     _c_p, _f64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "gmc_sgs_grid_values": (C.c_int, [C.c_int, C.c_int, C.c_int, _c_p, _c_p, _i64, C.c_int] + [_c_p] * 8),
     "gmc_mode_filter_binary": (C.c_int, [C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int, _c_p]),
     "gmc_launch_count": (_i64, [_c_p]),
     "gmc_step_kernel_info": (C.c_int, [_c_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -163,70 +163,10 @@ struct SgsWarpRec {
 };
 static_assert(8 * sizeof(SgsWarpRec) <= SGS_MAX_NEIGH * SGS_SIG_PITCH * sizeof(double), "warp records must fit in SgsShared::sig");
 
-template <bool INJECT>
-__device__ __forceinline__ void sgs_warp_node(const GmcDev& d, const SgsDev& s, const SgsShared& S, SgsWarpRec& R,
-                                              const double* __restrict__ z, int t_ord, int bw, const double* zn_in,
-                                              const Philox& rng, uint32_t it_lo, uint32_t it_hi) {
-    const int H = d.H, W = d.W, lane = threadIdx.x & 31;
-    const int x0 = S.x0, x1 = S.x1, y0 = S.y0, y1 = S.y1;
-    const int node = S.todo[t_ord];
-    const int bi = node / bw, bj = node - bi * bw;
-    const int i = x0 + bi, j = y0 + bj;
-    // (a) octant search, octants in the reference's order                                       neighbors.py:52-60
-    int n = 0;
-    for (int o = 0; o < 8; ++o) {
-        const int16_t* off = s.oct_off + (int64_t)o * s.lmax * 2;
-        const int cnt = __ldg(s.oct_cnt + o);
-        int found = 0;
-        for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
-            const int t = base + lane;
-            bool ok = false;
-            int di = 0, dj = 0, src = -1;
-            double v = 0.0;
-            if (t < cnt) {
-                if (t < SGS_NEAR) {
-                    const short2 o2 = S.near_off[o][t];
-                    di = o2.x;
-                    dj = o2.y;
-                } else {
-                    di = off[2 * t];
-                    dj = off[2 * t + 1];
-                }
-                const int ci = i + di, cj = j + dj;
-                if (ci >= 0 && ci < H && cj >= 0 && cj < W) {
-                    if (ci >= x0 && ci < x1 && cj >= y0 && cj < y1) {
-                        src = (ci - x0) * bw + (cj - y0);
-                        ok = S.ord[src] < t_ord;                 // radar cell (-1) or simulated earlier in the path
-                    } else {
-                        v = __ldcg(z + (int64_t)ci * W + cj);
-                        ok = (v == v);
-                    }
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, ok);
-            const int rank = found + __popc(m & ((1u << lane) - 1u));
-            if (ok && rank < s.per_oct) {
-                const int slot = n + rank;
-                R.ndi[slot] = (int16_t)di;
-                R.ndj[slot] = (int16_t)dj;
-                R.nsrc[slot] = (int16_t)src;
-                R.nval[slot] = v;
-            }
-            found += __popc(m);
-        }
-        n += min(found, s.per_oct);
-    }
-    if (lane == 0) {
-        R.n = n;
-        R.node = node;
-        R.kpath = S.todo_k[t_ord];
-        double zn, z1;
-        if (INJECT) zn = zn_in[S.todo_k[t_ord]];
-        else box_muller(rng((uint32_t)node, it_lo, it_hi, 6u), zn, z1);               // stream 6: node normals
-        R.zn = zn;
-    }
-    __syncwarp();
-    if (n == 0) return;                                      // reported by phase 2 (the reference would widen the radius)
+// Kriging weights and variance of one node from its n <= 48 neighbour offsets R.ndi/ndj (n > 0): assemble, eliminate,
+// Lagrange multiplier.  Results: R.w[0..n), R.var.  One warp; see the layout notes above.
+__device__ __forceinline__ void sgs_warp_solve(const SgsDev& s, SgsWarpRec& R, int n) {
+    const int lane = threadIdx.x & 31;
     // (b) assemble [Sigma | rho | 1] straight into registers                                       _krige.py:20-33
     const int lr = lane & 3, lc = lane >> 2;
     double A[12][7];
@@ -338,6 +278,73 @@ __device__ __forceinline__ void sgs_warp_node(const GmcDev& d, const SgsDev& s, 
     pv = warp_sum(pv);
     if (lane == 0) R.var = fabs(s.sill - pv);
     __syncwarp();
+}
+
+template <bool INJECT>
+__device__ __forceinline__ void sgs_warp_node(const GmcDev& d, const SgsDev& s, const SgsShared& S, SgsWarpRec& R,
+                                              const double* __restrict__ z, int t_ord, int bw, const double* zn_in,
+                                              const Philox& rng, uint32_t it_lo, uint32_t it_hi) {
+    const int H = d.H, W = d.W, lane = threadIdx.x & 31;
+    const int x0 = S.x0, x1 = S.x1, y0 = S.y0, y1 = S.y1;
+    const int node = S.todo[t_ord];
+    const int bi = node / bw, bj = node - bi * bw;
+    const int i = x0 + bi, j = y0 + bj;
+    // (a) octant search, octants in the reference's order                                       neighbors.py:52-60
+    int n = 0;
+    for (int o = 0; o < 8; ++o) {
+        const int16_t* off = s.oct_off + (int64_t)o * s.lmax * 2;
+        const int cnt = __ldg(s.oct_cnt + o);
+        int found = 0;
+        for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
+            const int t = base + lane;
+            bool ok = false;
+            int di = 0, dj = 0, src = -1;
+            double v = 0.0;
+            if (t < cnt) {
+                if (t < SGS_NEAR) {
+                    const short2 o2 = S.near_off[o][t];
+                    di = o2.x;
+                    dj = o2.y;
+                } else {
+                    di = off[2 * t];
+                    dj = off[2 * t + 1];
+                }
+                const int ci = i + di, cj = j + dj;
+                if (ci >= 0 && ci < H && cj >= 0 && cj < W) {
+                    if (ci >= x0 && ci < x1 && cj >= y0 && cj < y1) {
+                        src = (ci - x0) * bw + (cj - y0);
+                        ok = S.ord[src] < t_ord;                 // radar cell (-1) or simulated earlier in the path
+                    } else {
+                        v = __ldcg(z + (int64_t)ci * W + cj);
+                        ok = (v == v);
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            const int rank = found + __popc(m & ((1u << lane) - 1u));
+            if (ok && rank < s.per_oct) {
+                const int slot = n + rank;
+                R.ndi[slot] = (int16_t)di;
+                R.ndj[slot] = (int16_t)dj;
+                R.nsrc[slot] = (int16_t)src;
+                R.nval[slot] = v;
+            }
+            found += __popc(m);
+        }
+        n += min(found, s.per_oct);
+    }
+    if (lane == 0) {
+        R.n = n;
+        R.node = node;
+        R.kpath = S.todo_k[t_ord];
+        double zn, z1;
+        if (INJECT) zn = zn_in[S.todo_k[t_ord]];
+        else box_muller(rng((uint32_t)node, it_lo, it_hi, 6u), zn, z1);               // stream 6: node normals
+        R.zn = zn;
+    }
+    __syncwarp();
+    if (n == 0) return;                                      // reported by phase 2 (the reference would widen the radius)
+    sgs_warp_solve(s, R, n);
 }
 
 template <bool INJECT, bool WS>
@@ -1056,6 +1063,241 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
             c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
             cache_offset, resampled, err_flag);
     c->launches++;
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+// =====================================================================================================================
+// Whole-grid Sequential Gaussian Simulation: gstatsim_custom/interpolate.py:92-191, the generator of
+// the large-scale chains' initial beds (one realisation per chain, ~16 min each in the reference).
+//
+// A node's neighbour set and kriging weights depend on WHICH cells are conditioned when its turn comes - known from the
+// path alone - not on the simulated values.  So the simulation splits into
+//   1. sgs_grid_solve_kernel: all nodes of all realisations in parallel, one warp per node: octant search in the ORDER
+//      grid (ord[cell] = -1 for conditioning data, else the cell's position in the path; a cell is available to node t
+//      iff ord < t), kriging solve (sgs_warp_solve), record (neighbour cells, weights, sd) to global memory;
+//   2. sgs_grid_values_kernel: one warp per realisation walks its path: value = est + sd * noise with
+//      est = mean + sum w_i (v_i - mean) over the recorded neighbours (a sparse triangular solve), the truncated-normal
+//      draw when bounds are given (interpolate.py:166-181), writing the normal-score grid in place.
+// =====================================================================================================================
+struct SgsGridShared {
+    SgsWarpRec rec[8];
+    int cell[8][SGS_WN];
+    short2 near_off[8][SGS_NEAR];
+    int oct_cnt[8];
+};
+
+__global__ void __launch_bounds__(SGS_THREADS, 1)
+    sgs_grid_solve_kernel(SgsDev s, int H, int W, const int32_t* __restrict__ ord_all, const int32_t* __restrict__ path_all,
+                          int64_t n_path, int n_real, int32_t* __restrict__ rec_n, int32_t* __restrict__ rec_idx,
+                          double* __restrict__ rec_w, double* __restrict__ rec_sd, int32_t* err_out) {
+    extern __shared__ __align__(16) unsigned char sgs_raw[];
+    SgsGridShared& S = *reinterpret_cast<SgsGridShared*>(sgs_raw);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int t = tid; t < 8 * SGS_NEAR; t += SGS_THREADS) {
+        const int o = t / SGS_NEAR, k = t - o * SGS_NEAR;
+        short2 v = make_short2(0, 0);
+        if (k < s.lmax) v = make_short2(s.oct_off[((int64_t)o * s.lmax + k) * 2], s.oct_off[((int64_t)o * s.lmax + k) * 2 + 1]);
+        S.near_off[o][k] = v;
+    }
+    if (tid < 8) S.oct_cnt[tid] = s.oct_cnt[tid];
+    __syncthreads();
+    SgsWarpRec& R = S.rec[wid];
+    int* cellv = S.cell[wid];
+    const int64_t plane = (int64_t)H * W, total = (int64_t)n_real * n_path;
+    for (int64_t item = (int64_t)blockIdx.x * 8 + wid; item < total; item += (int64_t)gridDim.x * 8) {
+        const int r = (int)(item / n_path);
+        const int64_t t = item - (int64_t)r * n_path;
+        const int32_t* ord = ord_all + r * plane;
+        const int cell0 = path_all[r * n_path + t];
+        if (__ldg(ord + cell0) != (int32_t)t) {             // conditioning cell: nothing to simulate
+            if (lane == 0) rec_n[item] = -1;
+            continue;
+        }
+        const int i = cell0 / W, j = cell0 - i * W;
+        int n = 0;
+        for (int o = 0; o < 8; ++o) {                        // neighbors.py:52-60
+            const int16_t* off = s.oct_off + (int64_t)o * s.lmax * 2;
+            const int cnt = S.oct_cnt[o];
+            int found = 0;
+            for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
+                const int q = base + lane;
+                bool ok = false;
+                int di = 0, dj = 0, cell = 0;
+                if (q < cnt) {
+                    if (q < SGS_NEAR) {
+                        const short2 o2 = S.near_off[o][q];
+                        di = o2.x;
+                        dj = o2.y;
+                    } else {
+                        di = off[2 * q];
+                        dj = off[2 * q + 1];
+                    }
+                    const int ci = i + di, cj = j + dj;
+                    if (ci >= 0 && ci < H && cj >= 0 && cj < W) {
+                        cell = ci * W + cj;
+                        ok = __ldg(ord + cell) < (int32_t)t;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                const int rank = found + __popc(m & ((1u << lane) - 1u));
+                if (ok && rank < s.per_oct) {
+                    const int slot = n + rank;
+                    R.ndi[slot] = (int16_t)di;
+                    R.ndj[slot] = (int16_t)dj;
+                    cellv[slot] = cell;
+                }
+                found += __popc(m);
+            }
+            n += min(found, s.per_oct);
+        }
+        __syncwarp();
+        if (n == 0) {                                        // the reference would widen the radius by 100 km (:149-155)
+            if (lane == 0) {
+                rec_n[item] = 0;
+                rec_sd[item] = 0.0;
+                atomicOr(err_out, 1);
+            }
+            continue;
+        }
+        sgs_warp_solve(s, R, n);
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int q = lane + 32 * h2;
+            if (q < n) {
+                rec_idx[item * SGS_WN + q] = cellv[q];
+                rec_w[item * SGS_WN + q] = R.w[q];
+            }
+        }
+        if (lane == 0) {
+            rec_n[item] = n;
+            rec_sd[item] = sqrt(R.var);                      // interpolate.py:163 var = abs(var)
+        }
+        __syncwarp();
+    }
+}
+
+// inverse cdf of the standard normal restricted to [a, b] at probability u (what scipy's truncnorm.rvs applies to its one
+// uniform draw), through the survival function when both bounds lie in the upper tail
+__device__ __forceinline__ double truncnorm_ppf(double u, double a, double b) {
+    if (a > 0.0) {
+        const double sa = normcdf(-a), sb = normcdf(-b);
+        return -normcdfinv(sa - u * (sa - sb));
+    }
+    const double pa = normcdf(a), pb = normcdf(b);
+    return normcdfinv(pa + u * (pb - pa));
+}
+
+__global__ void __launch_bounds__(32)
+    sgs_grid_values_kernel(int H, int W, double* __restrict__ z_all, const int32_t* __restrict__ path_all, int64_t n_path,
+                           const int32_t* __restrict__ rec_n, const int32_t* __restrict__ rec_idx,
+                           const double* __restrict__ rec_w, const double* __restrict__ rec_sd,
+                           const double* __restrict__ noise_all, const double* __restrict__ blo, const double* __restrict__ bhi) {
+    const int r = blockIdx.x, lane = threadIdx.x;
+    const int64_t plane = (int64_t)H * W;
+    double* z = z_all + r * plane;
+    const int32_t* path = path_all + r * n_path;
+    const int64_t base = (int64_t)r * n_path;
+    for (int64_t t = 0; t < n_path; ++t) {
+        const int n = rec_n[base + t];
+        if (n < 0) continue;
+        const int cell = path[t];
+        double sv = 0.0, swv = 0.0, sw = 0.0;
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int q = lane + 32 * h2;
+            if (q < n) {
+                const int idx = __ldg(rec_idx + (base + t) * SGS_WN + q);
+                const double w = __ldg(rec_w + (base + t) * SGS_WN + q);
+                const double v = __ldcg(z + idx);
+                sv += v;
+                swv += w * v;
+                sw += w;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sv += __shfl_down_sync(0xffffffffu, sv, o);
+            swv += __shfl_down_sync(0xffffffffu, swv, o);
+            sw += __shfl_down_sync(0xffffffffu, sw, o);
+        }
+        if (lane == 0) {
+            double val = 0.0;
+            if (n > 0) {
+                const double mean = sv / (double)n;
+                const double est = mean + (swv - mean * sw);             // = mean + sum w (v - mean)     _krige.py:42
+                const double sd = rec_sd[base + t], nz = noise_all[base + t];
+                if (!blo) val = est + sd * nz;                           // rng.normal(est, sd)           :173
+                else {
+                    const double lo = blo[cell], hi = bhi[cell];
+                    if (lo == hi) val = lo;                              // :177-178
+                    else val = est + sd * truncnorm_ppf(nz, (lo - est) / sd, (hi - est) / sd);     // :180-181
+                }
+            }
+            __stcg(z + cell, val);
+        }
+        __threadfence_block();
+        __syncwarp();
+    }
+}
+
+// standalone normal-score transform (QuantileTransformer tables on the device): interpolate.py:185, utilities.py:21-24
+extern "C" int gmc_nst_transform(int device, const double* quantiles, const double* references, int n_quantiles,
+                                 const double* in, double* out, int64_t n, int inverse, void* stream) {
+    if (!quantiles || !references || !in || !out) GMC_FAIL(GMC_EINVAL, "gmc_nst_transform: NULL argument");
+    if (n_quantiles < 2 || n < 1) GMC_FAIL(GMC_EINVAL, "gmc_nst_transform: need >= 2 quantiles and >= 1 value");
+    GMC_CUDA(cudaSetDevice(device));
+    SgsDev s;
+    memset(&s, 0, sizeof(s));
+    s.quant = quantiles;
+    s.refs = references;
+    s.nq = n_quantiles;
+    sgs_transform_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(s, in, out, n, inverse);
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+extern "C" int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, const int32_t* path, int64_t n_path, int n_real,
+                                  const int16_t* oct_off, const int32_t* oct_cnt, int lmax, int hw, int num_points,
+                                  const double* lut, double sill, int32_t* rec_n, int32_t* rec_idx, double* rec_w,
+                                  double* rec_sd, int32_t* err_flag, void* stream) {
+    if (!ord || !path || !oct_off || !oct_cnt || !lut || !rec_n || !rec_idx || !rec_w || !rec_sd || !err_flag)
+        GMC_FAIL(GMC_EINVAL, "gmc_sgs_grid_solve: NULL argument");
+    if (H < 1 || W < 1 || n_path < 1 || n_path > (int64_t)H * W || n_real < 1) GMC_FAIL(GMC_ESHAPE, "gmc_sgs_grid_solve: bad sizes");
+    if (num_points < 8 || num_points > SGS_WN)
+        GMC_FAIL(GMC_EUNSUPPORTED, "gmc_sgs_grid_solve: num_points=%d outside [8,%d]", num_points, SGS_WN);
+    if (hw < 1 || lmax < 1) GMC_FAIL(GMC_EINVAL, "gmc_sgs_grid_solve: empty search stencil");
+    GMC_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    GMC_CUDA(cudaGetDeviceProperties(&prop, device));
+    SgsDev s;
+    memset(&s, 0, sizeof(s));
+    s.oct_off = oct_off;
+    s.oct_cnt = oct_cnt;
+    s.lmax = lmax;
+    s.hw = hw;
+    s.per_oct = num_points / 8;
+    s.lut = lut;
+    s.lut_w = 4 * hw + 1;
+    s.sill = sill;
+    GMC_CUDA(cudaFuncSetAttribute(sgs_grid_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SgsGridShared)));
+    const int64_t items = (int64_t)n_real * n_path;
+    const int ctas = (int)std::min<int64_t>((items + 7) / 8, (int64_t)prop.multiProcessorCount * 8);
+    sgs_grid_solve_kernel<<<ctas, SGS_THREADS, sizeof(SgsGridShared), (cudaStream_t)stream>>>(
+        s, H, W, ord, path, n_path, n_real, rec_n, rec_idx, rec_w, rec_sd, err_flag);
+    GMC_CUDA(cudaGetLastError());
+    return GMC_OK;
+}
+
+extern "C" int gmc_sgs_grid_values(int device, int H, int W, double* z, const int32_t* path, int64_t n_path, int n_real,
+                                   const int32_t* rec_n, const int32_t* rec_idx, const double* rec_w, const double* rec_sd,
+                                   const double* noise, const double* bound_lo, const double* bound_hi, void* stream) {
+    if (!z || !path || !rec_n || !rec_idx || !rec_w || !rec_sd || !noise) GMC_FAIL(GMC_EINVAL, "gmc_sgs_grid_values: NULL argument");
+    if ((bound_lo == nullptr) != (bound_hi == nullptr)) GMC_FAIL(GMC_EINVAL, "gmc_sgs_grid_values: give both bounds or neither");
+    if (H < 1 || W < 1 || n_path < 1 || n_real < 1) GMC_FAIL(GMC_ESHAPE, "gmc_sgs_grid_values: bad sizes");
+    GMC_CUDA(cudaSetDevice(device));
+    sgs_grid_values_kernel<<<n_real, 32, 0, (cudaStream_t)stream>>>(H, W, z, path, n_path, rec_n, rec_idx, rec_w, rec_sd, noise,
+                                                                    bound_lo, bound_hi);
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;
 }

@@ -35,7 +35,7 @@ def quiet(fn, *a, **k):
 # ---- the named trajectory cases: shared with tests/cases.py so oracle and reference see the same inputs ----
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from cases import (TRAJECTORY_CASES, FIELD_CASES, SGS_CASES, residual_case_inputs, build_case_grids,   # noqa: E402
-                   build_sgs_inputs, highvel_case_inputs)
+                   build_sgs_inputs, highvel_case_inputs, SGS_GRID_CASES, sgs_grid_inputs)
 
 
 def reference_chain(case):
@@ -95,6 +95,18 @@ def main():
         out = reference_sgs_chain(case)
         np.savez_compressed(os.path.join(OUT, f"sgs_{name}.npz"), **out)
         print(f"sgs_{name}: final loss {out['loss'][-1]!r}, acceptance {out['steps'].mean():.3f}")
+
+    # (6) whole-grid SGS realisations with bounds: gstatsim_custom/interpolate.sgs
+    from gstatsMCMC.gstatsim_custom import interpolate
+    import warnings
+    for name, case in SGS_GRID_CASES.items():
+        gi = sgs_grid_inputs(case)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sim = interpolate.sgs(gi["xx"], gi["yy"], gi["cond"], gi["vario"], radius=case["radius"], num_points=case["num_points"],
+                                  bounds=gi["bounds"], seed=np.random.default_rng(case["seed"]), quiet=True)
+        np.savez_compressed(os.path.join(OUT, f"sgs_grid_{name}.npz"), sim=sim)
+        print(f"sgs_grid_{name}: mean {np.nanmean(sim):.3f}, std {np.nanstd(sim):.3f}")
 
     # (5) region-mask preprocessing: Topography.get_highvel_boundary (the O(N^2) double loop, so a small grid)
     hb = highvel_case_inputs()

@@ -145,6 +145,86 @@ def sgs_block(xx, yy, grid, vario, radius, num_points, sim_mask, rng, record=Non
     return out
 
 
+def truncnorm_ppf(u, a, b):
+    """What scipy.stats.truncnorm.rvs applies to its one uniform draw (interpolate.py:181).  scipy evaluates it in log
+    space; the kernel uses  Phi^-1(Phi(a) + u (Phi(b) - Phi(a)))  (through the survival function when a > 0), which
+    agrees to rounding (tests/test_oracle_sgs.py)."""
+    from scipy.stats import truncnorm
+    return float(truncnorm.ppf(u, a, b))
+
+
+def truncnorm_ppf_direct(u, a, b):
+    """The closed form the kernel evaluates."""
+    if a > 0:                                   # both bounds in the upper tail: work with survival probabilities
+        sa, sb = norm.cdf(-a), norm.cdf(-b)
+        return -norm.ppf(sa - u * (sa - sb))
+    pa, pb = norm.cdf(a), norm.cdf(b)
+    return norm.ppf(pa + u * (pb - pa))
+
+
+def sgs_grid(xx, yy, grid, vario, radius, num_points, rng, bounds=None, n_quantiles=500, record=None, replay=None):
+    """Whole-grid Sequential Gaussian Simulation with bounds: gstatsim_custom/interpolate.py:92-191 (ktype='ok',
+    sim_mask=None, scalar variogram) with its `_preprocess` (:193-260) and utilities.gaussian_transformation (:7-26).
+
+    Returns (simulation in data units, NormalScore used).  record: dict that receives path [N,2], noise [N] (the standard
+    normal of an unbounded node / the uniform of a bounded one, NaN for conditioning cells) and the normal-score tables;
+    replay: dict(path, noise, quantiles, references) injects them instead of drawing from rng / refitting."""
+    from sklearn.preprocessing import QuantileTransformer
+    cond = ~np.isnan(grid)                                                                  # :207
+    if replay is None:
+        qt = QuantileTransformer(n_quantiles=n_quantiles, output_distribution="normal").fit(grid[cond].reshape(-1, 1))
+        nst = NormalScore(qt.quantiles_[:, 0].copy(), qt.references_.copy())
+    else:
+        nst = NormalScore(np.asarray(replay["quantiles"]), np.asarray(replay["references"]))
+    out = np.full(grid.shape, np.nan)
+    out[cond] = nst.forward(grid[cond])                                                     # utilities.py:21-24
+    ii, jj = np.meshgrid(np.arange(xx.shape[0]), np.arange(xx.shape[1]), indexing="ij")
+    inds = np.array([ii.flatten(), jj.flatten()]).T                                         # :214-215
+    tb = None
+    if bounds is not None:                                                                  # :233-252
+        tb = []
+        for bnd in bounds:
+            arr = np.full(xx.shape, float(bnd)) if np.isscalar(bnd) else np.asarray(bnd, dtype=np.float64)
+            tb.append(nst.forward(arr.reshape(-1)).reshape(xx.shape))
+    if replay is None:
+        rng.shuffle(inds)                                                                   # :125
+    else:
+        inds = np.array(replay["path"])
+    noise = np.full(inds.shape[0], np.nan)
+    hw0 = stencil_half_width(xx[0, :], radius)
+    for k in range(inds.shape[0]):
+        i, j = inds[k]
+        if cond[i, j]:
+            continue
+        rad, hw = radius, hw0
+        while True:                                                                         # :149-155
+            nearest = octant_neighbors(i, j, xx, yy, out, cond, rad, num_points, hw)
+            if nearest.shape[0] > 0:
+                break
+            rad += 100e3
+            hw = stencil_half_width(xx[0, :], rad)
+        est, var = ok_solve((xx[i, j], yy[i, j]), nearest, vario)
+        sd = np.sqrt(np.abs(var))                                                           # :163
+        if tb is None:
+            if replay is None:
+                draw = rng.normal(est, sd, 1)[0]
+                noise[k] = (draw - est) / sd if sd > 0 else 0.0
+            else:
+                noise[k] = replay["noise"][k]
+                draw = est + sd * noise[k]
+        elif tb[0][i, j] == tb[1][i, j]:                                                    # :177-178
+            draw = tb[0][i, j]
+        else:                                                                               # :180-181 truncnorm.rvs
+            a, b = (tb[0][i, j] - est) / sd, (tb[1][i, j] - est) / sd
+            noise[k] = rng.uniform() if replay is None else replay["noise"][k]
+            draw = est + sd * truncnorm_ppf(noise[k], a, b)
+        out[i, j] = draw
+        cond[i, j] = True
+    if record is not None:
+        record.update(path=inds.copy(), noise=noise, quantiles=nst.quantiles, references=nst.references)
+    return nst.inverse(out.reshape(-1)).reshape(xx.shape), nst                              # :185
+
+
 # ---- QuantileTransformer(output_distribution='normal') column transform      sklearn _data.py _transform_col ------
 @dataclass
 class NormalScore:

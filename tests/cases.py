@@ -115,6 +115,32 @@ SGS_CASES = {
 }
 
 
+# ---- whole-grid SGS realisations (gstatsim_custom/interpolate.sgs): initial beds of the large-scale chains -----------
+SGS_GRID_CASES = {
+    "free": dict(H=30, W=34, cond_frac=0.12, seed=11, radius=6e3, num_points=16, bounds=False,
+                 vario=dict(azimuth=0.0, nugget=0.0, major_range=4000.0, minor_range=4000.0, sill=1.0, s=1.2, vtype="matern")),
+    "bounded_k48": dict(H=40, W=36, cond_frac=0.2, seed=12, radius=5e3, num_points=48, bounds=True,
+                        vario=dict(azimuth=25.0, nugget=0.0, major_range=5000.0, minor_range=3000.0, sill=1.0, s=None,
+                                   vtype="exponential")),
+}
+
+
+def sgs_grid_inputs(case: dict) -> dict:
+    """Sparse conditioning data on a synthetic bed; bounds as in T2_StatisticalAnalysis (lower -9999, upper the surface,
+    here lowered so that the truncation binds at some nodes)."""
+    g = syn.make_grids(case["H"], case["W"])
+    r = np.random.default_rng(1000 + case["seed"])
+    cond = np.where(r.random((case["H"], case["W"])) < case["cond_frac"], g["bed0"], np.nan)
+    bounds = None
+    if case["bounds"]:
+        upper = np.where(np.isnan(cond), g["bed0"] + 40.0, np.maximum(cond, g["bed0"] + 40.0))
+        upper[5:9, 5:9] = -9999.0                  # lower == upper: the value is pinned (interpolate.py:177-178)
+        upper[np.isfinite(cond)] = np.maximum(upper[np.isfinite(cond)], cond[np.isfinite(cond)])
+        bounds = (np.full(cond.shape, -9999.0), upper)
+    v = {k: x for k, x in case["vario"].items() if x is not None}
+    return dict(xx=g["xx"], yy=g["yy"], cond=cond, bounds=bounds, vario=v)
+
+
 def build_sgs_inputs(case: dict) -> dict:
     """Grids + trend + fitted normal-score tables for an SGS case (tables come from sklearn, as in the tutorials)."""
     from scipy.ndimage import gaussian_filter
