@@ -101,7 +101,7 @@ def reference_main(a):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{cores} chains x {n_iter} iterations per step, numpy port of chain_crf.run (oracle/crf_oracle.py), one process per core"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -382,13 +382,29 @@ def gpu_main(a):
                         "ms_per_step": e2e_ms / a.steps, "api": "chain_crf.run_many(pinned host beds -> host beds, loss/step/block caches)"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stencil": stencil, "ensemble": ens,
                 "sgs": sgs, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict):
+    """The one JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _JSON_OUT
     a = parse()
+    # stdout carries exactly ONE JSON line: keep a private handle to it and point file descriptor 1 at stderr, so that
+    # anything a library prints (NCCL's version banner is written to fd 1 from C) cannot interleave with it
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         reference_main(a)
     else:
