@@ -123,3 +123,31 @@ def test_sgs_covariance_lut_matches_the_kriging_matrices():
         Sigma = S.covariance(vario["vtype"], squareform(pdist(xy @ R)), vario["sill"], vario["nugget"], vario.get("s"))
         mine = np.array([[lut[a[0] - b[0] + 2 * hw, a[1] - b[1] + 2 * hw] for b in pts] for a in pts])
         assert np.allclose(mine, Sigma, rtol=1e-12, atol=1e-13), vario["vtype"]
+
+
+def test_whole_grid_sgs_argument_checks_and_no_cpu_fallback():
+    """gstatsim_custom.interpolate.sgs validates like the reference (interpolate.py:262-330) and never computes on the CPU."""
+    import torch
+    from mcmc_gpu_b200._lib import GmcError
+    from mcmc_gpu_b200.gstatsim_custom import interpolate
+    xx, yy = np.meshgrid(np.arange(6) * 100.0, np.arange(5) * 100.0)
+    grid = np.full(xx.shape, np.nan)
+    grid[1, 2], grid[3, 4] = 1.0, 2.0
+    vario = dict(azimuth=0.0, nugget=0.0, major_range=300.0, minor_range=300.0, sill=1.0, vtype="exponential")
+    with pytest.raises(ValueError, match="Variogram missing"):
+        interpolate.sgs(xx, yy, grid, {"vtype": "exponential"})
+    with pytest.raises(ValueError, match="same shape"):
+        interpolate.sgs(xx, yy[:-1], grid, vario)
+    with pytest.raises(ValueError, match="Matern covariance requires"):
+        interpolate.sgs(xx, yy, grid, dict(vario, vtype="matern"))
+    with pytest.raises(ValueError, match="sim_mask"):
+        interpolate.sgs(xx, yy, grid, vario, sim_mask=np.ones((2, 2), dtype=bool))
+    with pytest.raises(NotImplementedError):
+        interpolate.sgs(xx, yy, grid, vario, ktype="sk")
+    with pytest.raises(NotImplementedError):
+        interpolate.sgs(xx, yy, grid, vario, num_points=64)
+    with pytest.raises(NotImplementedError):
+        interpolate.sgs(xx, yy, grid, dict(vario, sill=np.ones(xx.shape)))
+    if not torch.cuda.is_available():
+        with pytest.raises(GmcError, match="no CPU fallback"):
+            interpolate.sgs(xx, yy, grid, vario, radius=500.0, num_points=8, seed=1)
