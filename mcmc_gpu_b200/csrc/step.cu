@@ -24,6 +24,7 @@ struct SpecParams {
 struct StepScalars {
     int pair, h, w, ix, iy;
     int x0, x1, y0, y1, mx0, my0;
+    int tp, toff, tc0;     // candidate tile: row pitch (doubles), offset of column y0-1 inside a row, grid column of tile column 0
     double scale, nug, range_x, range_y, u;
     int accept;
     SpecParams spec;
@@ -343,9 +344,10 @@ struct StepTables {
     int16_t pos_y[GMC_MAX_EDGE], pos_w[GMC_MAX_EDGE / 2];
 };
 
-__device__ __forceinline__ void stage_tables(const GmcDev& d, const GmcPair& pr, StepTables& T) {
+__device__ __forceinline__ void stage_tables(const GmcDev& d, const GmcPair& pr, StepTables& T, int first = threadIdx.x,
+                                             int stride = GMC_STEP_THREADS) {
     const int h = pr.h, n2 = pr.w / 2;
-    for (int t = threadIdx.x; t < h; t += GMC_STEP_THREADS) {
+    for (int t = first; t < h; t += stride) {
         T.tw_h[t] = __ldg(d.twiddle + pr.ph.tw_off + t);
         T.pos_y[t] = __ldg(d.pos + pr.ph.pos_off + t);
         if (t <= h / 2) T.ksq_y[t] = __ldg(d.ksq + pr.ksq_off_h + t);
@@ -356,7 +358,7 @@ __device__ __forceinline__ void stage_tables(const GmcDev& d, const GmcPair& pr,
         }
         if (t <= n2) T.ksq_x[t] = __ldg(d.ksq + pr.ksq_off_w + t);
     }
-    for (int t = h + threadIdx.x; t <= n2; t += GMC_STEP_THREADS) {       // w/2 >= h (wide blocks)
+    for (int t = h + first; t <= n2; t += stride) {                       // w/2 >= h (wide blocks)
         if (t < n2) {
             T.tw_w[t] = __ldg(d.twiddle + pr.pw.tw_off + t);
             T.htw[t] = __ldg(d.twiddle + pr.pw.htw_off + t);
@@ -496,7 +498,9 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
 // ---------------------------------------------------------------------------------------------------------------
 // K4: the Metropolis step given f                                                        MCMC.py:1263-1360
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_window(StepScalars& s, int H, int W) {
+// vec: the bed rows can be staged with 16-byte copies (even W, 16-byte aligned base): the tile then starts at an even grid
+// column (one column left of y0-1 if needed) and has an even pitch
+__device__ __forceinline__ void block_window(StepScalars& s, int H, int W, bool vec) {
     // MCMC.py:1267-1276 (h, w even so h/2 is exact)
     const int h2 = s.h / 2, w2 = s.w / 2;
     s.x0 = max(0, s.ix - h2);
@@ -505,6 +509,16 @@ __device__ __forceinline__ void block_window(StepScalars& s, int H, int W) {
     s.y1 = min(W, s.iy + w2);
     s.mx0 = max(s.h - s.x1, 0);
     s.my0 = max(s.w - s.y1, 0);
+    const int bw = s.y1 - s.y0;
+    if (vec) {
+        s.tc0 = (s.y0 - 1) & ~1;                              // floor to even, also for -1 -> -2
+        s.toff = (s.y0 - 1) - s.tc0;
+        s.tp = (s.toff + bw + 3) & ~1;
+    } else {
+        s.tc0 = s.y0 - 1;
+        s.toff = 0;
+        s.tp = bw + 2;
+    }
 }
 
 __device__ __forceinline__ double sq_or_zero(double v) { return (v == v) ? mul_rn(v, v) : 0.0; }
@@ -514,6 +528,38 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+// ---- bulk asynchronous copies (TMA, 1-D) completing on an mbarrier: one instruction moves a whole tile row --------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
+}
+// orders earlier generic-proxy accesses of shared memory before later asynchronous-proxy (TMA) writes to it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -521,19 +567,55 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // one-cell halo lands asynchronously (cp.async) in the tile region, which is idle until the candidate is built; the
 // lines of the old block residual are pulled into L2.  Cells outside the grid become NaN (never used by the edge rules).
 __device__ __forceinline__ void stage_block_async(const StepScalars& s, int H, int W, const double* bed, const double* mcres,
-                                                  double* tile) {
-    const int bh = s.x1 - s.x0, bw = s.y1 - s.y0, tp = bw + 2;
+                                                  double* tile, bool vec, uint64_t* bar = nullptr) {
+    const int bh = s.x1 - s.x0, bw = s.y1 - s.y0, tp = s.tp;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (bar && vec) {
+        // One bulk copy per tile row (issued by one thread each: the per-instruction cost of cp.async, ~35 cycles of LSU
+        // time per warp instruction, was what this phase cost), one bulk L2 prefetch per row of the old residual.
+        // Columns [j_lo, j_hi) of the tile lie inside the grid: an even range, so every copy is 16-byte aligned and sized.
+        const int j_lo = max(s.tc0, 0), j_hi = min(s.tc0 + tp, W);
+        const int r_lo = max(s.x0 - 1, 0), r_hi = min(s.x1 + 1, H);
+        const unsigned bytes = (unsigned)(j_hi - j_lo) * 8u;
+        // rows are issued by the LAST threads of the CTA: the spectrum fill that follows hands the first threads one more
+        // trip than the last ones, so the few thousand cycles these instructions take disappear in that slack
+        const int rt = GMC_STEP_THREADS - 1 - (int)threadIdx.x;
+        if (rt == 0) mbar_arrive_expect_tx(bar, (unsigned)(r_hi - r_lo) * bytes);
+        for (int ti = rt; ti < bh + 2; ti += GMC_STEP_THREADS) {
+            const int i = s.x0 - 1 + ti;
+            double* dst = tile + ti * tp;
+            if (i >= r_lo && i < r_hi) {
+                fence_proxy_async();
+                bulk_g2s(dst + (j_lo - s.tc0), bed + (int64_t)i * W + j_lo, bytes, bar);
+                if (ti >= 1 && ti <= bh) bulk_prefetch_l2(mcres + (int64_t)i * W + j_lo, bytes);
+                for (int tj = 0; tj < j_lo - s.tc0; ++tj) dst[tj] = qnan;
+                for (int tj = j_hi - s.tc0; tj < tp; ++tj) dst[tj] = qnan;
+            } else {
+                for (int tj = 0; tj < tp; ++tj) dst[tj] = qnan;
+            }
+        }
+        return;
+    }
     for (int ti = wid; ti < bh + 2; ti += GMC_STEP_THREADS / 32) {          // one warp per tile row: coalesced
         const int i = s.x0 - 1 + ti;
         const bool row_in = i >= 0 && i < H;
-        const double* src = bed + (int64_t)i * W + (s.y0 - 1);
+        const double* src = bed + (int64_t)i * W + s.tc0;
         double* dst = tile + ti * tp;
-        for (int tj = lane; tj < tp; tj += 32) {
-            const int j = s.y0 - 1 + tj;
-            if (row_in && j >= 0 && j < W) cp_async8(dst + tj, src + tj);
-            else dst[tj] = qnan;
+        if (vec) {
+            // column pairs (tc0 + 2m, tc0 + 2m + 1): with W and tc0 even a pair is entirely inside or outside the grid;
+            // 16-byte copies halve the number of asynchronous-copy instructions, which is what this phase costs
+            for (int m = lane; 2 * m < tp; m += 32) {
+                const int j = s.tc0 + 2 * m;
+                if (row_in && j >= 0 && j < W) cp_async16(dst + 2 * m, src + 2 * m);
+                else dst[2 * m] = dst[2 * m + 1] = qnan;
+            }
+        } else {
+            for (int tj = lane; tj < tp; tj += 32) {
+                const int j = s.tc0 + tj;
+                if (row_in && j >= 0 && j < W) cp_async8(dst + tj, src + tj);
+                else dst[tj] = qnan;
+            }
         }
         if (ti >= 1 && ti <= bh) {                                          // old residual of this block row -> L2
             const char* base = reinterpret_cast<const char*>(mcres + (int64_t)i * W + s.y0);
@@ -544,21 +626,39 @@ __device__ __forceinline__ void stage_block_async(const StepScalars& s, int H, i
     cp_async_commit();
 }
 
+// What the helper warp of run_kernel prepares during the residual phase: the next step's scalars, block record, tables.
+struct StepTables;
+struct NextStep {
+    StepScalars* sc;
+    GmcPair* pair;
+    StepTables* tab;
+    uint64_t it;
+    bool vec;
+};
+__device__ void prepare_step(const GmcDev& d, const Philox& rng, uint64_t it, StepScalars& sc, GmcPair& s_pair, StepTables& s_tab,
+                             bool vec);
+
 // Field source for the tail: either the synthesised field in shared memory (FieldView) or an injected f in global memory.
-template <bool INJECT_F>
+// HELPER: the last warp does not take residual cells; it prepares the next step instead (run_kernel).
+template <bool INJECT_F, bool HELPER = false>
 __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, const FieldView& fv, const double* f_inj,
                           int f_pitch, const Philox& rng, uint32_t it_lo, uint32_t it_hi, double* tile, double* newres,
                           double* bed, double* mcres, double& ssq, int32_t* resampled, double* loss_next_out,
-                          PhaseClock& pc) {
+                          PhaseClock& pc, const NextStep* next = nullptr, uint64_t* tile_bar = nullptr, unsigned tile_parity = 0) {
     const int H = d.H, W = d.W;
     const StepScalars s = *sc;
     const int bh = s.x1 - s.x0, bw = s.y1 - s.y0;
-    const int tp = bw + 2;
+    const int tp = s.tp;
+    tile += s.toff;                                           // tile[(bi+1)*tp + (bj+1)] is the cell (x0+bi, y0+bj)
     const FastDiv dbw(bw);
 
     // phase A: candidate = bed + perturbation on the gated block cells (the tile already holds the bed, staged
     // asynchronously at the top of the step); loads are issued in batches so one L2 round trip serves U cells.
-    cp_async_wait_all();
+    if (tile_bar) {
+        unsigned spins = 0;
+        while (!mbar_try_wait(tile_bar, tile_parity))
+            if (++spins > (1u << 22)) break;                  // cannot happen (byte counts match by construction); never hang
+    } else cp_async_wait_all();
     __syncthreads();
     {
         constexpr int U = 8;
@@ -601,7 +701,9 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
     // phase B: residual on the block, loss delta, thickness guard                       MCMC.py:1292-1329
     double delta = 0.0;
     int bad = 0;
-    for (int e = threadIdx.x; e < bh * bw; e += GMC_STEP_THREADS) {
+    constexpr int B_THREADS = HELPER ? GMC_STEP_THREADS - 32 : GMC_STEP_THREADS;
+    if (HELPER && threadIdx.x >= B_THREADS) prepare_step(d, rng, next->it, *next->sc, *next->pair, *next->tab, next->vec);
+    for (int e = (HELPER && threadIdx.x >= B_THREADS) ? bh * bw : threadIdx.x; e < bh * bw; e += B_THREADS) {
         const int bi = dbw.div(e), bj = e - bi * bw;
         const int i = s.x0 + bi, j = s.y0 + bj;
         const double* tc = tile + (bi + 1) * tp + (bj + 1);
@@ -681,6 +783,52 @@ __device__ double resync_ssq(const GmcDev& d, const double* mcres, double* scrat
     return block_sum<GMC_STEP_THREADS>(acc, scratch);
 }
 
+// Everything a step needs before its field can be synthesised, computed by ONE warp: the step's scalars (block size, scale,
+// nugget, range, centre, acceptance uniform, spectral constants), the block size's record and its small tables.  Nothing
+// here depends on the chain state, so run_kernel lets a helper warp prepare step k+1 while the other warps are in the
+// latency-bound residual phase of step k (the tables of step k are dead by then).
+__device__ __noinline__ void prepare_step(const GmcDev& d, const Philox& rng, uint64_t it, StepScalars& sc, GmcPair& s_pair,
+                                          StepTables& s_tab, bool vec) {
+    const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
+    const int l = threadIdx.x & 31;
+    // the five Philox blocks of the step's scalars are drawn by five lanes in parallel, then gathered by lane 0
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (l < 5) r = rng(l < 3 ? (uint32_t)l : (uint32_t)(l - 3), it_lo, it_hi, l < 3 ? GMC_STREAM_RF_SCALARS : GMC_STREAM_CHAIN);
+    uint4 g[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        g[k] = make_uint4(__shfl_sync(0xffffffffu, r.x, k), __shfl_sync(0xffffffffu, r.y, k),
+                          __shfl_sync(0xffffffffu, r.z, k), __shfl_sync(0xffffffffu, r.w, k));
+    if (l == 0) {
+        const GmcFieldModel& fm = d.fm;
+        const uint4 r0 = g[0], r1 = g[1], r2 = g[2], c0 = g[3], c1 = g[4];
+        // RandField stream: block size, scale, nugget, range(s)                   MCMC.py:755, 200-207
+        sc.pair = (int)bounded_u64(r0.x, r0.y, (uint64_t)d.n_pairs);
+        sc.scale = div_rn(add_rn(fm.scale_min, mul_rn(sub_rn(fm.scale_max, fm.scale_min), u01_halfopen(r0.z, r0.w))), 3.0);
+        sc.nug = add_rn(0.0, mul_rn(fm.nugget_max, u01_halfopen(r1.x, r1.y)));
+        sc.range_x = add_rn(fm.range_min_x, mul_rn(sub_rn(fm.range_max_x, fm.range_min_x), u01_halfopen(r1.z, r1.w)));
+        if (fm.isotropic) sc.range_y = sc.range_x;
+        else sc.range_y = add_rn(fm.range_min_y, mul_rn(sub_rn(fm.range_max_y, fm.range_min_y), u01_halfopen(r2.x, r2.y)));
+        // chain stream: block centre (uniform over the allowed cells) and the acceptance uniform   MCMC.py:1253-1261, 1336
+        if (d.n_centre_cells > 0) {
+            const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
+            sc.ix = cell / d.W;
+            sc.iy = cell - sc.ix * d.W;
+        } else {
+            sc.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
+            sc.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
+        }
+        sc.u = u01_halfopen(c1.x, c1.y);
+        s_pair = d.pairs[sc.pair];             // one trip: sizes, table offsets and both FFT plans
+        sc.h = s_pair.h;
+        sc.w = s_pair.w;
+        block_window(sc, d.H, d.W, vec);
+        sc.spec = make_spec(fm, sc.range_x, sc.range_y);
+    }
+    __syncwarp();
+    stage_tables(d, s_pair, s_tab, l, 32);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------------
@@ -692,9 +840,10 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
                int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int resync_every, int tile_off,
                long long* phase_acc) {
     __shared__ double scratch[40];
-    __shared__ StepScalars sc;
+    __shared__ StepScalars sc, sc_next;
     __shared__ GmcPair s_pair;
     __shared__ StepTables s_tab;
+    __shared__ __align__(8) uint64_t tile_bar;                // completion barrier of the bulk copies that stage the bed tile
     double* buf = reinterpret_cast<double*>(gmc_smem);
     const int c = blockIdx.x;
     const int64_t plane = (int64_t)d.H * d.W;
@@ -706,63 +855,40 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
     PhaseClock pc;
     pc.acc = phase_acc;
     pc.start();
+    if (threadIdx.x == 0) mbar_init(&tile_bar, 1);
 
+    const bool vec = (d.W % 2 == 0) && ((reinterpret_cast<uintptr_t>(bed_all) & 15) == 0);
+    // step iter0 is prepared up front; every later step by the helper warp during the previous step's residual phase
+    if (threadIdx.x < 32) prepare_step(d, rng, iter0, sc_next, s_pair, s_tab, vec);
+    __syncthreads();
+    if (threadIdx.x == 0) sc = sc_next;
+    __syncthreads();
+    // iterations until the next re-sum of the tracked residual (it % resync_every == 0), counted down instead of a
+    // 64-bit modulo per step
+    int64_t to_resync = -1;
+    if (resync_every > 0) to_resync = (int64_t)((uint64_t)resync_every - iter0 % (uint64_t)resync_every) % resync_every;
     for (int k = 0; k < n_steps; ++k) {
         const uint64_t it = iter0 + (uint64_t)k;
         const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
-        if (resync_every > 0 && it % (uint64_t)resync_every == 0) ssq = resync_ssq(d, mcres, scratch);
-        if (threadIdx.x < 32) {
-            // the five Philox blocks of the step's scalars are drawn by five lanes in parallel, then gathered by lane 0
-            const int l = threadIdx.x;
-            uint4 r = make_uint4(0, 0, 0, 0);
-            if (l < 5) r = rng(l < 3 ? (uint32_t)l : (uint32_t)(l - 3), it_lo, it_hi, l < 3 ? GMC_STREAM_RF_SCALARS : GMC_STREAM_CHAIN);
-            uint4 g[5];
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                g[k] = make_uint4(__shfl_sync(0xffffffffu, r.x, k), __shfl_sync(0xffffffffu, r.y, k),
-                                  __shfl_sync(0xffffffffu, r.z, k), __shfl_sync(0xffffffffu, r.w, k));
-            if (l == 0) {
-                const GmcFieldModel& fm = d.fm;
-                const uint4 r0 = g[0], r1 = g[1], r2 = g[2], c0 = g[3], c1 = g[4];
-                // RandField stream: block size, scale, nugget, range(s)                   MCMC.py:755, 200-207
-                sc.pair = (int)bounded_u64(r0.x, r0.y, (uint64_t)d.n_pairs);
-                sc.scale = div_rn(add_rn(fm.scale_min, mul_rn(sub_rn(fm.scale_max, fm.scale_min), u01_halfopen(r0.z, r0.w))), 3.0);
-                sc.nug = add_rn(0.0, mul_rn(fm.nugget_max, u01_halfopen(r1.x, r1.y)));
-                sc.range_x = add_rn(fm.range_min_x, mul_rn(sub_rn(fm.range_max_x, fm.range_min_x), u01_halfopen(r1.z, r1.w)));
-                if (fm.isotropic) sc.range_y = sc.range_x;
-                else sc.range_y = add_rn(fm.range_min_y, mul_rn(sub_rn(fm.range_max_y, fm.range_min_y), u01_halfopen(r2.x, r2.y)));
-                // chain stream: block centre (uniform over the allowed cells) and the acceptance uniform   MCMC.py:1253-1261, 1336
-                if (d.n_centre_cells > 0) {
-                    const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
-                    sc.ix = cell / d.W;
-                    sc.iy = cell - sc.ix * d.W;
-                } else {
-                    sc.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
-                    sc.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
-                }
-                sc.u = u01_halfopen(c1.x, c1.y);
-                s_pair = d.pairs[sc.pair];             // one trip: sizes, table offsets and both FFT plans
-                sc.h = s_pair.h;
-                sc.w = s_pair.w;
-                block_window(sc, d.H, d.W);
-                sc.spec = make_spec(fm, sc.range_x, sc.range_y);
-            }
+        if (to_resync == 0) {
+            ssq = resync_ssq(d, mcres, scratch);
+            to_resync = resync_every;
         }
-        __syncthreads();
-        stage_tables(d, s_pair, s_tab);
-        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off);
-        __syncthreads();
+        --to_resync;
+        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off, vec, vec ? &tile_bar : nullptr);
         pc.mark(0);
         const FieldView fv = synth_field<false>(d, buf, scratch, s_pair, s_tab, sc.scale, sc.nug, sc.spec, rng, it_lo, it_hi,
                                                 nullptr, nullptr, nullptr, true, pc);
         // tile after the field; the new residuals reuse the field's storage once the tile is built (f is dead by then)
-        step_tail<false>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
-                         nullptr, pc);
+        const NextStep next = {&sc_next, &s_pair, &s_tab, it + 1, vec};
+        step_tail<false, true>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
+                               nullptr, pc, &next, vec ? &tile_bar : nullptr, (unsigned)k & 1u);
         if (threadIdx.x == 0) {
             const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
             if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
             if (step_cache) step_cache[slot] = (uint8_t)sc.accept;
             if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(sc.ix, sc.iy, sc.h, sc.w);
+            sc = sc_next;                      // nobody reads sc between the tail's last barrier and the one below
         }
         __syncthreads();
     }
@@ -779,6 +905,8 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS)
     double* buf = reinterpret_cast<double*>(gmc_smem);
     const int c = blockIdx.x;
     const int64_t plane = (int64_t)d.H * d.W;
+    // 16-byte tile staging needs an even offset of the tile inside the dynamic shared memory as well
+    const bool vec = (d.W % 2 == 0) && ((reinterpret_cast<uintptr_t>(bed_all) & 15) == 0) && (((int64_t)hmax * wmax) % 2 == 0);
     if (threadIdx.x == 0) {
         sc.h = hw[2 * c];
         sc.w = hw[2 * c + 1];
@@ -786,12 +914,12 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS)
         sc.iy = centre[2 * c + 1];
         sc.u = u[c];
         sc.pair = -1;
-        block_window(sc, d.H, d.W);
+        block_window(sc, d.H, d.W, vec);
     }
     __syncthreads();
     double ssq = ssq_all[c];
     const Philox rng(0ull);
-    stage_block_async(sc, d.H, d.W, bed_all + c * plane, mcres_all + c * plane, buf + (int64_t)hmax * wmax);
+    stage_block_async(sc, d.H, d.W, bed_all + c * plane, mcres_all + c * plane, buf + (int64_t)hmax * wmax, vec);
     FieldView fv = {};
     PhaseClock pc;
     pc.acc = nullptr;
@@ -1026,6 +1154,7 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
     int32_t* resampled = resampled_all ? resampled_all + c * plane : nullptr;
     const Philox rng(seeds[c]);
     double ssq = ssq_all[c];
+    const bool vec = (d.W % 2 == 0) && ((reinterpret_cast<uintptr_t>(bed_all) & 15) == 0) && (tile_off % 2 == 0);
     PhaseClock pc;
     pc.acc = nullptr;
 
@@ -1062,13 +1191,13 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
             s_pair = d.pairs[sc.pair];
             sc.h = s_pair.h;
             sc.w = s_pair.w;
-            block_window(sc, d.H, d.W);
+            block_window(sc, d.H, d.W, vec);
             s_rp = make_randmeth(fm, n_modes, sc.range_x, sc.range_y, angle);
         }
         __syncthreads();
         const FieldView fv = synth_randmeth<false>(d, buf, tab_off, s_pair, res, sc.scale, sc.nug, s_rp, rng, it_lo, it_hi,
                                                    nullptr, nullptr, true);
-        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off);
+        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off, vec);
         step_tail<false>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
                          nullptr, pc);
         if (threadIdx.x == 0) {
@@ -1085,7 +1214,7 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
 // ---------------------------------------------------------------------------------------------------------------
 // host entry points
 // ---------------------------------------------------------------------------------------------------------------
-static size_t tile_bytes(int h, int w) { return (size_t)(h + 2) * (w + 2) * sizeof(double); }
+static size_t tile_bytes(int h, int w) { return (size_t)(h + 2) * (w + 4) * sizeof(double); }   // pitch <= w + 4 (aligned staging)
 static size_t field_bytes(const GmcPair& p) { return (size_t)p.h * p.pitchc * sizeof(double2); }
 
 int gmc_step_configure(gmc_ctx* c) {
