@@ -294,7 +294,7 @@ def gpu_main(a):
     achieved = bytes_last / (step_ms[-1] * 1e-3) / 1e9
     # DRAM bytes per chain-step of this kernel from the committed ncu --set full capture (profiles/r1/run_kernel.ncu.txt:
     # 757.8 MB read + 234.6 MB written over 256 chains x 40 iterations), scaled to this launch's chain-steps
-    ncu_traffic_per_chain_step = (756.346368e6 + 229.425152e6) / (256 * 40)
+    ncu_traffic_per_chain_step = (766.582528e6 + 250.255872e6) / (256 * 40)
     roofline = {"kernel": "run_kernel (fused K1 field synthesis + K4 Metropolis step)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_chain_step * C * n_it,
                 "traffic_source": "profiles/r1/run_kernel.ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum per chain-step x chain-steps per launch)",
