@@ -139,6 +139,7 @@ struct gmc_ctx {
     double field_res;      // grid spacing of the proposal fields (gmc_set_blocks)
     int64_t launches;
     long long* d_phase;    // optional per-phase cycle counters of run_kernel (debug)
+    int* d_sched;          // run_kernel work counter + per-chain completed-chunk counts (launches with C > resident CTAs)
     gmc_sgs_state* sgs;    // small-scale (SGS) chain tables, see sgs.cu
 };
 

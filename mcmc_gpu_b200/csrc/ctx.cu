@@ -66,6 +66,7 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->field_res = 0.0;
     c->launches = 0;
     c->d_phase = nullptr;
+    c->d_sched = nullptr;
     c->sgs = nullptr;
     c->dev.H = H;
     c->dev.W = W;
@@ -89,6 +90,7 @@ extern "C" int gmc_destroy(gmc_ctx* c) {
     cudaFree(c->d_ksq);
     cudaFree(c->d_edge_masks);
     cudaFree(c->d_phase);
+    cudaFree(c->d_sched);
     gmc_sgs_destroy(c);
     delete c;
     return GMC_OK;

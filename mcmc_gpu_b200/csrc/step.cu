@@ -12,6 +12,7 @@
 //       block only, the loss changes by the block's delta, and accept/reject plus in-place write-back happen without leaving
 //       the kernel (MCMC.py:1263-1360).  HBM sees the bed halo tile, the old block residual and, on accept, the write-back.
 #include "common.cuh"
+#include <cstdlib>
 
 struct SpecParams {
     int model;
@@ -765,7 +766,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
             const int64_t idx = (int64_t)(s.x0 + bi) * W + (s.y0 + bj);
             __stcg(bed + idx, tile[(bi + 1) * tp + (bj + 1)]);
             __stcg(mcres + idx, newres[e]);
-            if (resampled && (__ldg(d.flags + idx) & FLAG_GATE)) resampled[idx] += 1;
+            if (resampled && (__ldg(d.flags + idx) & FLAG_GATE)) __stcg(resampled + idx, __ldcg(resampled + idx) + 1);
         }
     }
     __syncthreads();   // write-back visible to the next iteration's tile load; smem free for reuse
@@ -834,65 +835,105 @@ __device__ __noinline__ void prepare_step(const GmcDev& d, const Philox& rng, ui
 // ---------------------------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char gmc_smem[];
 
+// sched (may be NULL): work distribution for launches with more chains than resident CTAs.  Without it CTA b advances
+// chain b by all n_steps.  With it the iterations are cut into chunks of `chunk` and the (chunk, chain) items - chunk-major,
+// so that a chain's previous chunk was handed out gridDim.x * ... items earlier - are drawn from the counter sched[0]; an
+// item waits until its chain has completed the previous chunk (sched[1 + chain]).  Every CTA of the grid is resident and an
+// item only ever waits for an item drawn earlier, so the waits cannot deadlock.  A chain migrates between CTAs (and SMs):
+// its state is written with L2 stores + __threadfence() before the completion count is published, and read back only
+// through L2 (TMA bulk copies, ld.cg).
 __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
     run_kernel(GmcDev d, double* bed_all, double* mcres_all, double* ssq_all, const uint64_t* __restrict__ seeds,
                uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache,
                int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int resync_every, int tile_off,
-               long long* phase_acc) {
+               long long* phase_acc, int C, int* sched, int chunk) {
     __shared__ double scratch[40];
     __shared__ StepScalars sc, sc_next;
     __shared__ GmcPair s_pair;
     __shared__ StepTables s_tab;
     __shared__ __align__(8) uint64_t tile_bar;                // completion barrier of the bulk copies that stage the bed tile
+    __shared__ long long s_item;
     double* buf = reinterpret_cast<double*>(gmc_smem);
-    const int c = blockIdx.x;
     const int64_t plane = (int64_t)d.H * d.W;
-    double* bed = bed_all + c * plane;
-    double* mcres = mcres_all + c * plane;
-    int32_t* resampled = resampled_all ? resampled_all + c * plane : nullptr;
-    const Philox rng(seeds[c]);
-    double ssq = ssq_all[c];
     PhaseClock pc;
     pc.acc = phase_acc;
     pc.start();
     if (threadIdx.x == 0) mbar_init(&tile_bar, 1);
-
     const bool vec = (d.W % 2 == 0) && ((reinterpret_cast<uintptr_t>(bed_all) & 15) == 0);
-    // step iter0 is prepared up front; every later step by the helper warp during the previous step's residual phase
-    if (threadIdx.x < 32) prepare_step(d, rng, iter0, sc_next, s_pair, s_tab, vec);
-    __syncthreads();
-    if (threadIdx.x == 0) sc = sc_next;
-    __syncthreads();
-    // iterations until the next re-sum of the tracked residual (it % resync_every == 0), counted down instead of a
-    // 64-bit modulo per step
-    int64_t to_resync = -1;
-    if (resync_every > 0) to_resync = (int64_t)((uint64_t)resync_every - iter0 % (uint64_t)resync_every) % resync_every;
-    for (int k = 0; k < n_steps; ++k) {
-        const uint64_t it = iter0 + (uint64_t)k;
-        const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
-        if (to_resync == 0) {
-            ssq = resync_ssq(d, mcres, scratch);
-            to_resync = resync_every;
+    const int n_chunks = sched ? (n_steps + chunk - 1) / chunk : 1;
+    const long long n_items = (long long)n_chunks * C;
+    unsigned tile_uses = 0;                                   // phase parity of tile_bar
+
+    for (long long item = blockIdx.x;; item += gridDim.x) {
+        if (sched) {
+            if (threadIdx.x == 0) {
+                const long long it2 = atomicAdd(reinterpret_cast<unsigned int*>(sched), 1u);
+                if (it2 < n_items) {
+                    const int cc = (int)(it2 % C), jj = (int)(it2 / C);
+                    volatile int* done = sched + 1 + cc;
+                    unsigned spins = 0;
+                    while (*done < jj) {
+                        __nanosleep(200);
+                        if (++spins > (1u << 26)) break;      // cannot happen (see above); never hang the device
+                    }
+                    __threadfence();
+                }
+                s_item = it2;
+            }
+            __syncthreads();
+            item = s_item;
         }
-        --to_resync;
-        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off, vec, vec ? &tile_bar : nullptr);
-        pc.mark(0);
-        const FieldView fv = synth_field<false>(d, buf, scratch, s_pair, s_tab, sc.scale, sc.nug, sc.spec, rng, it_lo, it_hi,
-                                                nullptr, nullptr, nullptr, true, pc);
-        // tile after the field; the new residuals reuse the field's storage once the tile is built (f is dead by then)
-        const NextStep next = {&sc_next, &s_pair, &s_tab, it + 1, vec};
-        step_tail<false, true>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
-                               nullptr, pc, &next, vec ? &tile_bar : nullptr, (unsigned)k & 1u);
-        if (threadIdx.x == 0) {
-            const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
-            if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
-            if (step_cache) step_cache[slot] = (uint8_t)sc.accept;
-            if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(sc.ix, sc.iy, sc.h, sc.w);
-            sc = sc_next;                      // nobody reads sc between the tail's last barrier and the one below
-        }
+        if (item >= n_items) break;
+        const int c = (int)(item % C), j = (int)(item / C);
+        const int k0 = sched ? j * chunk : 0, k1 = sched ? min(n_steps, k0 + chunk) : n_steps;
+        double* bed = bed_all + c * plane;
+        double* mcres = mcres_all + c * plane;
+        int32_t* resampled = resampled_all ? resampled_all + c * plane : nullptr;
+        const Philox rng(seeds[c]);
+        double ssq = __ldcg(ssq_all + c);
+
+        // step k0 is prepared up front; every later step by the helper warp during the previous step's residual phase
+        if (threadIdx.x < 32) prepare_step(d, rng, iter0 + (uint64_t)k0, sc_next, s_pair, s_tab, vec);
         __syncthreads();
+        if (threadIdx.x == 0) sc = sc_next;
+        __syncthreads();
+        // iterations until the next re-sum of the tracked residual (it % resync_every == 0), counted down instead of a
+        // 64-bit modulo per step
+        int64_t to_resync = -1;
+        if (resync_every > 0)
+            to_resync = (int64_t)((uint64_t)resync_every - (iter0 + (uint64_t)k0) % (uint64_t)resync_every) % resync_every;
+        for (int k = k0; k < k1; ++k) {
+            const uint64_t it = iter0 + (uint64_t)k;
+            const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
+            if (to_resync == 0) {
+                ssq = resync_ssq(d, mcres, scratch);
+                to_resync = resync_every;
+            }
+            --to_resync;
+            stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off, vec, vec ? &tile_bar : nullptr);
+            pc.mark(0);
+            const FieldView fv = synth_field<false>(d, buf, scratch, s_pair, s_tab, sc.scale, sc.nug, sc.spec, rng, it_lo, it_hi,
+                                                    nullptr, nullptr, nullptr, true, pc);
+            // tile after the field; the new residuals reuse the field's storage once the tile is built (f is dead by then)
+            const NextStep next = {&sc_next, &s_pair, &s_tab, it + 1, vec};
+            step_tail<false, true>(d, &sc, scratch, fv, nullptr, 0, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq,
+                                   resampled, nullptr, pc, &next, vec ? &tile_bar : nullptr, tile_uses & 1u);
+            ++tile_uses;
+            if (threadIdx.x == 0) {
+                const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
+                if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
+                if (step_cache) step_cache[slot] = (uint8_t)sc.accept;
+                if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(sc.ix, sc.iy, sc.h, sc.w);
+                sc = sc_next;                  // nobody reads sc between the tail's last barrier and the one below
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) __stcg(ssq_all + c, ssq);
+        if (!sched) break;
+        __threadfence();                                      // this thread's state writes are visible device-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(sched + 1 + c, j + 1);   // ... before the chain's next chunk may start anywhere
     }
-    if (threadIdx.x == 0) ssq_all[c] = ssq;
 }
 
 __global__ void __launch_bounds__(GMC_STEP_THREADS)
@@ -1355,10 +1396,22 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
         GMC_CUDA(cudaGetLastError());
         return GMC_OK;
     }
-    run_kernel<<<C, GMC_STEP_THREADS, c->step_smem_bytes, (cudaStream_t)stream>>>(c->dev, bed, mcres, ssq, seeds, iter0, n_steps,
-                                                                                 loss_cache, step_cache, blocks_cache,
-                                                                                 cache_stride, cache_offset, resampled,
-                                                                                 resync_every, c->step_tile_off, c->d_phase);
+    // more chains than resident CTAs: cut the run into (chunk, chain) items handed out dynamically, so that the tail of the
+    // last wave does not idle the GPU (e.g. 512 chains on 296 slots: 1.73 instead of 2 waves)
+    const int slots = std::max(1, c->step_ctas_per_sm) * c->sm_count;
+    const bool vec = (c->W % 2 == 0) && (((uintptr_t)bed & 15) == 0);
+    int grid = C, chunk = n_steps;
+    int* sched = nullptr;
+    if (C > slots && vec && n_steps > 1 && !getenv("GMC_STATIC_SCHED")) {
+        if (!c->d_sched) GMC_CUDA(cudaMalloc(&c->d_sched, (size_t)(c->max_chains + 1) * sizeof(int)));
+        GMC_CUDA(cudaMemsetAsync(c->d_sched, 0, (size_t)(C + 1) * sizeof(int), (cudaStream_t)stream));
+        sched = c->d_sched;
+        grid = slots;
+        chunk = std::max(4, (n_steps + 31) / 32);
+    }
+    run_kernel<<<grid, GMC_STEP_THREADS, c->step_smem_bytes, (cudaStream_t)stream>>>(
+        c->dev, bed, mcres, ssq, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride, cache_offset, resampled,
+        resync_every, c->step_tile_off, c->d_phase, C, sched, chunk);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;

@@ -169,3 +169,25 @@ def test_pipelined_run_many_equals_plain_run_many():
     assert bits_equal(res["bed"].numpy(), plain["bed"])
     assert np.array_equal(res["steps"].numpy(), plain["steps"]) and np.array_equal(res["blocks"].numpy()[:, 1:], plain["blocks"][:, 1:].astype(np.int32))
     assert np.allclose(res["loss"].numpy(), plain["loss"], rtol=1e-13, atol=0)
+
+
+def test_more_chains_than_cta_slots_uses_chunked_scheduling_and_stays_bit_identical(monkeypatch):
+    """With more chains than resident CTAs the launch hands out (chunk, chain) items dynamically and chains migrate
+    between CTAs; every trajectory must equal the one-CTA-per-chain schedule bit for bit."""
+    import torch
+    from mcmc_gpu_b200.MCMC import ChainBatch
+    case = dict(TRAJECTORY_CASES["ragged_rf"])
+    ch, rf, g = product_chain(case)
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    C = 2 * sm * 2 + 37                                     # more than any plausible number of resident CTAs
+    beds0 = np.stack([g["bed0"] + 0.01 * (k % 11) for k in range(C)])
+    keys = [1000 + 7 * k for k in range(C)]
+    a = ChainBatch(ch, rf, beds0, keys, track_resampled=True)
+    la, sa, ba = a.advance(57, resync_every=16)
+    monkeypatch.setenv("GMC_STATIC_SCHED", "1")             # read by gmc_run
+    b = ChainBatch(ch, rf, beds0, keys, track_resampled=True)
+    lb, sb, bb = b.advance(57, resync_every=16)
+    assert bits_equal(a.beds(), b.beds())
+    assert np.array_equal(sa, sb) and np.array_equal(ba, bb) and bits_equal(la, lb)
+    assert np.array_equal(a.resampled_times(), b.resampled_times())
+    assert 0.05 < sa.mean() < 0.98
