@@ -770,7 +770,7 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
             const double c = S.cand[e];
             __stcg(bedc + idx, c);
             __stcg(z + idx, nst_forward(s, c));          // the reference re-transforms the accepted bed every step (MCMC.py:1767)
-            if (resampled) resampled[idx] += 1;          // MCMC.py:1806
+            if (resampled) __stcg(resampled + idx, __ldcg(resampled + idx) + 1);          // MCMC.py:1806
         }
         for (int e = tid; e < rh * rw; e += SGS_THREADS) {
             const int ri = e / rw, rj = e - ri * rw;
@@ -835,57 +835,90 @@ __global__ void __launch_bounds__(SGS_THREADS)
     }
 }
 
+// sched (may be NULL): as in run_kernel (step.cu) - with more chains than resident CTAs the iterations are cut into chunks
+// and the (chunk, chain) items are drawn from sched[0]; sched[1 + chain] counts the chain's completed chunks.  The chain
+// state already travels through L2 only (ld.cg / st.cg), so a chain may continue on any CTA.
 template <bool WS>
 __global__ void __launch_bounds__(SGS_THREADS)
     sgs_run_kernel(GmcDev d, SgsDev s, double* bedc_all, double* z_all, double* mcres_all, double* ssq_all, int32_t* nviol_all,
                    const uint64_t* __restrict__ seeds, uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache,
-                   int32_t* blocks_cache, int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int32_t* err_out) {
+                   int32_t* blocks_cache, int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int32_t* err_out,
+                   int C, int* sched, int chunk) {
     extern __shared__ __align__(16) unsigned char sgs_raw[];
     SgsShared& S = *reinterpret_cast<SgsShared*>(sgs_raw);
-    const int c = blockIdx.x;
+    __shared__ long long s_item;
     const int64_t plane = (int64_t)d.H * d.W;
-    const Philox rng(seeds[c]);
-    double ssq = ssq_all[c];
-    int nviol = nviol_all[c];
     if (threadIdx.x == 0) S.err = 0;
     sgs_stage_offsets(s, S);
-    for (int k = 0; k < n_steps; ++k) {
-        const uint64_t it = iter0 + (uint64_t)k;
-        const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
-        if (threadIdx.x == 0) {
-            // chain stream: centre (uniform over region cells), block sizes (upper bound exclusive), acceptance uniform
-            const uint4 c0 = rng(0u, it_lo, it_hi, GMC_STREAM_CHAIN);
-            const uint4 c1 = rng(1u, it_lo, it_hi, GMC_STREAM_CHAIN);
-            const uint4 c2 = rng(2u, it_lo, it_hi, GMC_STREAM_CHAIN);
-            if (d.n_centre_cells > 0) {
-                const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
-                S.ix = cell / d.W;
-                S.iy = cell - S.ix * d.W;
-            } else {
-                S.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
-                S.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
+    const int n_chunks = sched ? (n_steps + chunk - 1) / chunk : 1;
+    const long long n_items = (long long)n_chunks * C;
+    for (long long item = blockIdx.x;; item += gridDim.x) {
+        if (sched) {
+            if (threadIdx.x == 0) {
+                const long long it2 = atomicAdd(reinterpret_cast<unsigned int*>(sched), 1u);
+                if (it2 < n_items) {
+                    volatile int* done = sched + 1 + (int)(it2 % C);
+                    const int jj = (int)(it2 / C);
+                    unsigned spins = 0;
+                    while (*done < jj) {
+                        __nanosleep(200);
+                        if (++spins > (1u << 26)) break;      // cannot happen: an item only waits for items drawn earlier
+                    }
+                    __threadfence();
+                }
+                s_item = it2;
             }
-            S.u = u01_halfopen(c1.x, c1.y);
-            S.bsx = s.bmin_x + (int)bounded_u64(c2.x, c2.y, (uint64_t)(s.bmax_x - s.bmin_x));
-            S.bsy = s.bmin_y + (int)bounded_u64(c2.z, c2.w, (uint64_t)(s.bmax_y - s.bmin_y));
-            sgs_window(S, d.H, d.W);
+            __syncthreads();
+            item = s_item;
         }
-        __syncthreads();
-        sgs_one_step<false, WS>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, nullptr, nullptr,
-                            rng, it_lo, it_hi, resampled_all ? resampled_all + c * plane : nullptr, nullptr);
+        if (item >= n_items) break;
+        const int c = (int)(item % C), j = (int)(item / C);
+        const int k0 = sched ? j * chunk : 0, k1 = sched ? min(n_steps, k0 + chunk) : n_steps;
+        const Philox rng(seeds[c]);
+        double ssq = __ldcg(ssq_all + c);
+        int nviol = __ldcg(nviol_all + c);
+        for (int k = k0; k < k1; ++k) {
+            const uint64_t it = iter0 + (uint64_t)k;
+            const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
+            if (threadIdx.x == 0) {
+                // chain stream: centre (uniform over region cells), block sizes (upper bound exclusive), acceptance uniform
+                const uint4 c0 = rng(0u, it_lo, it_hi, GMC_STREAM_CHAIN);
+                const uint4 c1 = rng(1u, it_lo, it_hi, GMC_STREAM_CHAIN);
+                const uint4 c2 = rng(2u, it_lo, it_hi, GMC_STREAM_CHAIN);
+                if (d.n_centre_cells > 0) {
+                    const int32_t cell = d.centre_cells[bounded_u64(c0.x, c0.y, (uint64_t)d.n_centre_cells)];
+                    S.ix = cell / d.W;
+                    S.iy = cell - S.ix * d.W;
+                } else {
+                    S.ix = (int)bounded_u64(c0.x, c0.y, (uint64_t)d.H);
+                    S.iy = (int)bounded_u64(c0.z, c0.w, (uint64_t)d.W);
+                }
+                S.u = u01_halfopen(c1.x, c1.y);
+                S.bsx = s.bmin_x + (int)bounded_u64(c2.x, c2.y, (uint64_t)(s.bmax_x - s.bmin_x));
+                S.bsy = s.bmin_y + (int)bounded_u64(c2.z, c2.w, (uint64_t)(s.bmax_y - s.bmin_y));
+                sgs_window(S, d.H, d.W);
+            }
+            __syncthreads();
+            sgs_one_step<false, WS>(d, s, S, bedc_all + c * plane, z_all + c * plane, mcres_all + c * plane, ssq, nviol, nullptr,
+                                    nullptr, rng, it_lo, it_hi, resampled_all ? resampled_all + c * plane : nullptr, nullptr);
+            if (threadIdx.x == 0) {
+                const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
+                if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
+                if (step_cache) step_cache[slot] = (uint8_t)S.accept;
+                if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(S.ix, S.iy, S.bsx, S.bsy);
+            }
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
-            const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
-            if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
-            if (step_cache) step_cache[slot] = (uint8_t)S.accept;
-            if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(S.ix, S.iy, S.bsx, S.bsy);
+            __stcg(ssq_all + c, ssq);
+            __stcg(nviol_all + c, nviol);
         }
+        if (!sched) break;
+        __threadfence();
         __syncthreads();
+        if (threadIdx.x == 0) atomicExch(sched + 1 + c, j + 1);
     }
-    if (threadIdx.x == 0) {
-        ssq_all[c] = ssq;
-        nviol_all[c] = nviol;
-        if (err_out && S.err) atomicOr(err_out, 1);
-    }
+    if (threadIdx.x == 0 && err_out && S.err) atomicOr(err_out, 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1054,14 +1087,30 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
         GMC_FAIL(GMC_ESHAPE, "gmc_sgs_run: cache window exceeds stride");
     if (n_steps == 0) return GMC_OK;
     c->sgs->dev.phase = c->d_phase;
+    // more chains than resident CTAs: dynamic (chunk, chain) items, see sgs_run_kernel
+    int per_sm = 0;
     if (c->sgs->warp_solver)
-        sgs_run_kernel<true><<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
-            c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
-            cache_offset, resampled, err_flag);
+        GMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgs_run_kernel<true>, SGS_THREADS, sizeof(SgsShared)));
     else
-        sgs_run_kernel<false><<<C, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
+        GMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sgs_run_kernel<false>, SGS_THREADS, sizeof(SgsShared)));
+    const int slots = std::max(1, per_sm) * c->sm_count;
+    int grid = C, chunk = n_steps;
+    int* sched = nullptr;
+    if (C > slots && n_steps > 1 && !getenv("GMC_STATIC_SCHED")) {
+        if (!c->d_sched) GMC_CUDA(cudaMalloc(&c->d_sched, (size_t)(c->max_chains + 1) * sizeof(int)));
+        GMC_CUDA(cudaMemsetAsync(c->d_sched, 0, (size_t)(C + 1) * sizeof(int), (cudaStream_t)stream));
+        sched = c->d_sched;
+        grid = slots;
+        chunk = std::max(2, (n_steps + 31) / 32);
+    }
+    if (c->sgs->warp_solver)
+        sgs_run_kernel<true><<<grid, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
             c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
-            cache_offset, resampled, err_flag);
+            cache_offset, resampled, err_flag, C, sched, chunk);
+    else
+        sgs_run_kernel<false><<<grid, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
+            c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
+            cache_offset, resampled, err_flag, C, sched, chunk);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;

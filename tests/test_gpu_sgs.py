@@ -113,3 +113,21 @@ def test_small_scale_driver_layout_and_resume(tmp_path):
         # resume re-derives bedc = bed - trend from the saved full bed: one rounding of (x + t) - t per cell
         assert np.abs(final[k] - r2[k][0]).max() <= 1e-9 * np.abs(final[k]).max()
         assert len(r1[k]) == 7 and r1[k][3].shape == (6,)
+
+
+def test_more_chains_than_resident_ctas_is_bit_identical_to_the_static_schedule(monkeypatch):
+    """sgs_run_kernel hands out (chunk, chain) items dynamically when the launch has more chains than resident CTAs."""
+    import torch
+    from mcmc_gpu_b200 import MCMC
+    case = SGS_CASES["matern_nst"]
+    ch, g = product_sgs_chain(case)
+    C = 2 * torch.cuda.get_device_properties(0).multi_processor_count + 5
+    beds0 = np.stack([g["bed_init"] + 0.01 * (k % 7) for k in range(C)])
+    keys = [MCMC.philox_key(500 + k) for k in range(C)]
+    a = MCMC.SgsBatch(ch, beds0, keys)
+    la, sa, ba = a.advance(9)
+    monkeypatch.setenv("GMC_STATIC_SCHED", "1")
+    b = MCMC.SgsBatch(ch, beds0, keys)
+    lb, sb, bb = b.advance(9)
+    assert bits_equal(a.beds(), b.beds()) and np.array_equal(sa, sb) and np.array_equal(ba, bb) and bits_equal(la, lb)
+    assert np.isfinite(la).all()
