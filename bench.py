@@ -293,14 +293,16 @@ def gpu_main(a):
     launch_ms = float(np.mean(step_ms))
     achieved = bytes_last / (step_ms[-1] * 1e-3) / 1e9
     # DRAM bytes per chain-step of this kernel from the committed ncu --set full capture (profiles/r1/run_kernel.ncu.txt:
-    # 757.8 MB read + 234.6 MB written over 256 chains x 40 iterations), scaled to this launch's chain-steps
+    # 766.6 MB read + 250.3 MB written over 256 chains x 40 iterations), scaled to this launch's chain-steps
     ncu_traffic_per_chain_step = (766.582528e6 + 250.255872e6) / (256 * 40)
     roofline = {"kernel": "run_kernel (fused K1 field synthesis + K4 Metropolis step)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic_per_chain_step * C * n_it,
                 "traffic_source": "profiles/r1/run_kernel.ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum per chain-step x chain-steps per launch)",
                 "algorithmic_bytes_per_launch": float(bytes_last), "peak_source": peak_src,
                 "algorithmic_bytes_per_chain_step": float(bytes_last) / (C * n_it), "launch_ms": launch_ms,
-                "note": "U3 block-local formulation; this kernel is FP64/shared-memory bound, not HBM bound (DESIGN.md)"}
+                "note": "U3 block-local formulation; this kernel is FP64 latency / issue bound, not HBM bound (DESIGN.md)",
+                "ncu": {"ipc_per_sm": 1.71, "issue_slots_pct": 47.3, "fp64_pipe_pct": 18.1, "dram_throughput_pct": 7.6,
+                        "warps_per_sm": 16, "source": "profiles/r1/run_kernel.ncu.txt (ncu --set full, same kernel, 256 chains x 40 iterations)"}}
 
     # ---- (2) the stencil metric: fused full-grid residual + masked loss (U2) and residual write (U1) ----------------
     loss_d = torch.empty(C, dtype=torch.float64, device=dev)
