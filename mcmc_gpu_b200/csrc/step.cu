@@ -565,8 +565,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Start the tail's HBM traffic at the top of the step, while the field is synthesised: the bed of the block plus its
-// one-cell halo lands asynchronously (cp.async) in the tile region, which is idle until the candidate is built; the
-// lines of the old block residual are pulled into L2.  Cells outside the grid become NaN (never used by the edge rules).
+// one-cell halo lands asynchronously in the tile region, which is idle until the candidate is built - by TMA bulk copies
+// completing on an mbarrier when `bar` is given (run_kernel, even W), else by cp.async - and the lines of the old block
+// residual are pulled into L2.  Cells outside the grid become NaN (never used by the edge rules).
 __device__ __forceinline__ void stage_block_async(const StepScalars& s, int H, int W, const double* bed, const double* mcres,
                                                   double* tile, bool vec, uint64_t* bar = nullptr) {
     const int bh = s.x1 - s.x0, bw = s.y1 - s.y0, tp = s.tp;
