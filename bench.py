@@ -115,6 +115,16 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        # NVML from a sampling thread (a query takes well under a millisecond, so a 40 ms step gets several samples);
+        # the nvidia-smi loop (>= 100 ms per row) is the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle, self.stop_flag = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index), False
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -122,11 +132,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        bits = [("hw_slowdown", getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+        reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        try:
+            sm_max = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        except Exception:
+            sm_max = 0
+        while not self.stop_flag:
+            try:
+                mask = int(reasons_fn(self.handle))
+                row = [str(self.index), str(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)), str(sm_max),
+                       str(n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0), hex(mask)]
+                row += ["Active" if mask & b else "Not Active" for _, b in bits]
+                self.rows.append((time.perf_counter(), row))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.rows.append((time.perf_counter(), [x.strip() for x in ln.split(",")]))
 
     def stop(self):
+        if getattr(self, "nvml", None):
+            self.stop_flag = True
         if self.proc:
             self.proc.terminate()
 
