@@ -209,13 +209,15 @@ GMC_API int gmc_nst_transform(int device, const double* quantiles, const double*
 /* Kriging records of n_real realisations (the loop body of interpolate.py:130-163 without the draw), all nodes in parallel:
  *   ord  dev [n_real][H*W] i32 : -1 at conditioning cells, else the cell's position in the realisation's path
  *   path dev [n_real][n_path] i32 : row-major cell indices in simulation order (the shuffled `inds`, :125)
- *   oct_off / oct_cnt / lmax / hw : octant search lists as for gmc_sgs_setup (neighbors.py:52-60);  lut : covariance of
- *   integer offsets, [(4hw+1)^2];  num_points <= 48
+ *   oct_off / lmax / hw : octant search lists as for gmc_sgs_setup (neighbors.py:52-60), built for the WIDEST radius;
+ *   oct_cnt dev [n_levels][8] : per radius level (radius, radius + 100 km, ...: the reference widens the search of a node
+ *   that finds no data, interpolate.py:149-155) the number of list entries closer than that radius;  n_levels <= 4
+ *   lut : covariance of integer offsets, [(4hw+1)^2];  num_points <= 48
  *   rec_n [n_real][n_path] i32 (-1: conditioning cell), rec_idx, rec_w [n_real][n_path][48], rec_sd [n_real][n_path]
- *   err_flag dev i32: bit 0 set if a node found no neighbour within the radius (the reference widens it by 100 km). */
+ *   err_flag dev i32: bit 0 set if a node found no neighbour even within the widest radius. */
 GMC_API int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, const int32_t* path, int64_t n_path, int n_real,
-                       const int16_t* oct_off, const int32_t* oct_cnt, int lmax, int hw, int num_points, const double* lut,
-                       double sill, int32_t* rec_n, int32_t* rec_idx, double* rec_w, double* rec_sd, int32_t* err_flag,
+                       const int16_t* oct_off, const int32_t* oct_cnt, int n_levels, int lmax, int hw, int num_points,
+                       const double* lut, double sill, int32_t* rec_n, int32_t* rec_idx, double* rec_w, double* rec_sd, int32_t* err_flag,
                        void* stream);
 
 /* The draws in path order (interpolate.py:166-183): z dev [n_real][H*W] holds the normal-scored data (anything elsewhere)

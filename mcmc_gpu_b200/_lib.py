@@ -59,7 +59,7 @@ PROTOTYPES = {
     "gmc_min_dist": (C.c_int, [C.c_int, _c_p, _c_p, _i64, _c_p, _c_p, _i64, _c_p, _c_p]),
     "gmc_nst_transform": (C.c_int, [C.c_int, _c_p, _c_p, C.c_int, _c_p, _c_p, _i64, C.c_int, _c_p]),
     "gmc_sgs_grid_solve": (C.c_int, [C.c_int, C.c_int, C.c_int, _c_p, _c_p, _i64, C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int,
-                                     _c_p, _f64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
+                                     C.c_int, _c_p, _f64, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "gmc_sgs_grid_values": (C.c_int, [C.c_int, C.c_int, C.c_int, _c_p, _c_p, _i64, C.c_int] + [_c_p] * 8),
     "gmc_mode_filter_binary": (C.c_int, [C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int, _c_p]),
     "gmc_launch_count": (_i64, [_c_p]),

@@ -1129,16 +1129,17 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
 //      est = mean + sum w_i (v_i - mean) over the recorded neighbours (a sparse triangular solve), the truncated-normal
 //      draw when bounds are given (interpolate.py:166-181), writing the normal-score grid in place.
 // =====================================================================================================================
+#define SGS_MAX_LEVELS 4           // search radii radius, radius + 100 km, ... (interpolate.py:149-155)
 struct SgsGridShared {
     SgsWarpRec rec[8];
     int cell[8][SGS_WN];
     short2 near_off[8][SGS_NEAR];
-    int oct_cnt[8];
+    int oct_cnt[SGS_MAX_LEVELS][8];
 };
 
 __global__ void __launch_bounds__(SGS_THREADS, 1)
     sgs_grid_solve_kernel(SgsDev s, int H, int W, const int32_t* __restrict__ ord_all, const int32_t* __restrict__ path_all,
-                          int64_t n_path, int n_real, int32_t* __restrict__ rec_n, int32_t* __restrict__ rec_idx,
+                          int64_t n_path, int n_real, int n_levels, int32_t* __restrict__ rec_n, int32_t* __restrict__ rec_idx,
                           double* __restrict__ rec_w, double* __restrict__ rec_sd, int32_t* err_out) {
     extern __shared__ __align__(16) unsigned char sgs_raw[];
     SgsGridShared& S = *reinterpret_cast<SgsGridShared*>(sgs_raw);
@@ -1149,7 +1150,7 @@ __global__ void __launch_bounds__(SGS_THREADS, 1)
         if (k < s.lmax) v = make_short2(s.oct_off[((int64_t)o * s.lmax + k) * 2], s.oct_off[((int64_t)o * s.lmax + k) * 2 + 1]);
         S.near_off[o][k] = v;
     }
-    if (tid < 8) S.oct_cnt[tid] = s.oct_cnt[tid];
+    if (tid < 8 * n_levels) S.oct_cnt[tid >> 3][tid & 7] = s.oct_cnt[tid];      // prefix lengths of the lists per radius level
     __syncthreads();
     SgsWarpRec& R = S.rec[wid];
     int* cellv = S.cell[wid];
@@ -1165,9 +1166,12 @@ __global__ void __launch_bounds__(SGS_THREADS, 1)
         }
         const int i = cell0 / W, j = cell0 - i * W;
         int n = 0;
+        // the lists are sorted by distance, so "all offsets closer than the level's radius" is a prefix; a node that finds
+        // nothing within `radius` searches again with radius + 100 km, as the reference does (interpolate.py:149-155)
+        for (int lev = 0; lev < n_levels && n == 0; ++lev)
         for (int o = 0; o < 8; ++o) {                        // neighbors.py:52-60
             const int16_t* off = s.oct_off + (int64_t)o * s.lmax * 2;
-            const int cnt = S.oct_cnt[o];
+            const int cnt = S.oct_cnt[lev][o];
             int found = 0;
             for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
                 const int q = base + lane;
@@ -1201,7 +1205,7 @@ __global__ void __launch_bounds__(SGS_THREADS, 1)
             n += min(found, s.per_oct);
         }
         __syncwarp();
-        if (n == 0) {                                        // the reference would widen the radius by 100 km (:149-155)
+        if (n == 0) {                                        // nothing even within the widest radius the caller provided
             if (lane == 0) {
                 rec_n[item] = 0;
                 rec_sd[item] = 0.0;
@@ -1307,7 +1311,7 @@ extern "C" int gmc_nst_transform(int device, const double* quantiles, const doub
 }
 
 extern "C" int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, const int32_t* path, int64_t n_path, int n_real,
-                                  const int16_t* oct_off, const int32_t* oct_cnt, int lmax, int hw, int num_points,
+                                  const int16_t* oct_off, const int32_t* oct_cnt, int n_levels, int lmax, int hw, int num_points,
                                   const double* lut, double sill, int32_t* rec_n, int32_t* rec_idx, double* rec_w,
                                   double* rec_sd, int32_t* err_flag, void* stream) {
     if (!ord || !path || !oct_off || !oct_cnt || !lut || !rec_n || !rec_idx || !rec_w || !rec_sd || !err_flag)
@@ -1316,6 +1320,8 @@ extern "C" int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, 
     if (num_points < 8 || num_points > SGS_WN)
         GMC_FAIL(GMC_EUNSUPPORTED, "gmc_sgs_grid_solve: num_points=%d outside [8,%d]", num_points, SGS_WN);
     if (hw < 1 || lmax < 1) GMC_FAIL(GMC_EINVAL, "gmc_sgs_grid_solve: empty search stencil");
+    if (n_levels < 1 || n_levels > SGS_MAX_LEVELS)
+        GMC_FAIL(GMC_EINVAL, "gmc_sgs_grid_solve: n_levels=%d outside [1,%d]", n_levels, SGS_MAX_LEVELS);
     GMC_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
     GMC_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -1333,7 +1339,7 @@ extern "C" int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, 
     const int64_t items = (int64_t)n_real * n_path;
     const int ctas = (int)std::min<int64_t>((items + 7) / 8, (int64_t)prop.multiProcessorCount * 8);
     sgs_grid_solve_kernel<<<ctas, SGS_THREADS, sizeof(SgsGridShared), (cudaStream_t)stream>>>(
-        s, H, W, ord, path, n_path, n_real, rec_n, rec_idx, rec_w, rec_sd, err_flag);
+        s, H, W, ord, path, n_path, n_real, n_levels, rec_n, rec_idx, rec_w, rec_sd, err_flag);
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;
 }

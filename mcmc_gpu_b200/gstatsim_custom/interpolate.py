@@ -19,6 +19,8 @@ from .. import _lib
 from ..sgs_tables import covariance_lut, grid_steps, octant_stencil
 
 MAX_POINTS = 48
+MAX_LEVELS = 4            # search radii: radius, +100 km, +200 km, +300 km
+MAX_HALF_WIDTH = 700      # cells; bounds the offset lists and the covariance table ((4 hw + 1)^2 doubles)
 
 
 def _generator(seed):
@@ -139,7 +141,17 @@ def sgs_many(xx, yy, grid, variogram, seeds, radius=100e3, num_points=20, ktype=
     path_d, ord_d, noise_d = cu(paths, torch.int32), cu(ords, torch.int32), cu(noise)
 
     dx, dy = grid_steps(xx, yy)
-    off, cnt, hw = octant_stencil(dx, dy, radius)
+    # A node that finds no data within `radius` searches again with radius + 100 km (interpolate.py:149-155).  The octant
+    # lists are sorted by distance, so every radius level is a prefix of the lists built for the widest one; levels stop
+    # once the radius covers the grid diagonal (or after MAX_LEVELS, or when the tables would get unreasonably large).
+    diag = float(np.hypot(abs(dx) * W, abs(dy) * H))
+    radii = [float(radius)]
+    while radii[-1] < diag and len(radii) < MAX_LEVELS and (radii[-1] + 100e3) / min(abs(dx), abs(dy)) <= MAX_HALF_WIDTH:
+        radii.append(radii[-1] + 100e3)
+    off, cnt_max, hw = octant_stencil(dx, dy, radii[-1])
+    dist = np.sqrt((off[..., 1] * dx) ** 2 + (off[..., 0] * dy) ** 2)         # [8, lmax], the reference's expression
+    valid = np.arange(off.shape[1])[None, :] < cnt_max[:, None]
+    cnt = np.stack([((dist < r) & valid).sum(1) for r in radii]).astype(np.int32)   # [levels, 8]
     vario = {k: (v.lower() if k == "vtype" else float(v)) for k, v in variogram.items()}
     lut = covariance_lut(dx, dy, hw, vario)
     off_d, cnt_d, lut_d = cu(off, torch.int16), cu(cnt, torch.int32), cu(lut)
@@ -150,7 +162,7 @@ def sgs_many(xx, yy, grid, variogram, seeds, radius=100e3, num_points=20, ktype=
     rec_sd = torch.empty(items, dtype=torch.float64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.check(lib.gmc_sgs_grid_solve(dev.index, H, W, ord_d.data_ptr(), path_d.data_ptr(), n_path, n_real, off_d.data_ptr(),
-                                      cnt_d.data_ptr(), int(off.shape[1]), int(hw), int(num_points), lut_d.data_ptr(),
+                                      cnt_d.data_ptr(), int(cnt.shape[0]), int(off.shape[1]), int(hw), int(num_points), lut_d.data_ptr(),
                                       float(vario["sill"]), rec_n.data_ptr(), rec_idx.data_ptr(), rec_w.data_ptr(),
                                       rec_sd.data_ptr(), err.data_ptr(), st))
     z = z0[None].repeat(n_real, 1).contiguous()
@@ -158,8 +170,8 @@ def sgs_many(xx, yy, grid, variogram, seeds, radius=100e3, num_points=20, ktype=
                                        rec_idx.data_ptr(), rec_w.data_ptr(), rec_sd.data_ptr(), noise_d.data_ptr(),
                                        blo.data_ptr() if blo is not None else None, bhi.data_ptr() if bhi is not None else None, st))
     if int(err.item()) & 1:
-        raise NotImplementedError("a node found no conditioning data within `radius`; the reference would widen the search "
-                                  "by 100 km (interpolate.py:149-155) - pass a larger radius")
+        raise NotImplementedError(f"a node found no conditioning data within {radii[-1] / 1e3:.0f} km (the search was widened "
+                                  f"{len(radii) - 1} times by 100 km, interpolate.py:149-155) - pass a larger radius")
     sim = transform(z.reshape(-1), True).reshape(n_real, H, W)
     return sim if as_tensor else sim.cpu().numpy()
 

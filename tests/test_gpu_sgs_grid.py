@@ -65,11 +65,24 @@ def test_sim_mask_and_loud_errors():
     out = interpolate.sgs(gi["xx"], gi["yy"], gi["cond"], gi["vario"], radius=case["radius"], num_points=16, sim_mask=mask, seed=1)
     data = np.isfinite(gi["cond"])
     assert np.isfinite(out[mask | data]).all() and np.isnan(out[~mask & ~data]).all()
-    corner = np.full(gi["cond"].shape, np.nan)
-    corner[:3, :3] = np.arange(9.0).reshape(3, 3)
-    with pytest.raises(NotImplementedError):                  # path nodes far from the only data find nothing within 1 km
-        interpolate.sgs(gi["xx"], gi["yy"], corner, gi["vario"], radius=1e3, num_points=16, seed=1)
     with pytest.raises(ValueError):
         interpolate.sgs(gi["xx"], gi["yy"], gi["cond"], {"vtype": "matern"}, seed=1)
     with pytest.raises(NotImplementedError):
         interpolate.sgs(gi["xx"], gi["yy"], gi["cond"], gi["vario"], ktype="sk", seed=1)
+
+
+def test_search_radius_is_widened_like_the_reference_when_a_node_finds_no_data():
+    """Data in one corner only and a 1.5 km radius: most nodes find nothing at first and search again with
+    radius + 100 km (interpolate.py:149-155).  Same seed -> the oracle's realisation."""
+    case = SGS_GRID_CASES["free"]
+    gi = sgs_grid_inputs(case)
+    corner = np.full(gi["cond"].shape, np.nan)
+    corner[:6, :7] = gi["cond"][:6, :7]
+    corner[2, 3], corner[4, 1], corner[0, 5] = 310.0, 295.0, 330.0
+    from mcmc_gpu_b200.gstatsim_custom import interpolate
+    got = interpolate.sgs(gi["xx"], gi["yy"], corner, gi["vario"], radius=1.5e3, num_points=16, seed=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ora, _ = S.sgs_grid(gi["xx"], gi["yy"], corner, gi["vario"], 1.5e3, 16, np.random.default_rng(5))
+    assert np.isfinite(got).all()
+    assert np.abs(got - ora).max() <= TOL * np.abs(ora).max()
