@@ -353,6 +353,11 @@ class chain:
             ctx = Context(H, W, max_chains, device)
             ctx.set_static(**self._static_args())
             if RF is not None:
+                if int(np.max(RF.pairs[1])) > H or int(np.max(RF.pairs[0])) > W:
+                    # a block cut by BOTH edges of the grid: the reference's slices f[mxmin:mxmax] and bed[bxmin:bxmax]
+                    # (MCMC.py:1267-1276) then differ in length and numpy raises on the first such proposal
+                    raise ValueError(f"operands could not be broadcast together: a {int(np.max(RF.pairs[1]))}x"
+                                     f"{int(np.max(RF.pairs[0]))} proposal block does not fit the {H}x{W} grid")
                 ctx.set_field_model(RF.model_name, RF.smoothness, RF.isotropic, RF.range_min_x, RF.range_max_x,
                                     RF.range_min_y, RF.range_max_y, RF.scale_min, RF.scale_max, RF.nugget_max)
                 ctx.set_blocks(RF.pairs, RF.edge_masks, RF.resolution)

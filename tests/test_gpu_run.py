@@ -191,3 +191,13 @@ def test_more_chains_than_cta_slots_uses_chunked_scheduling_and_stays_bit_identi
     assert np.array_equal(sa, sb) and np.array_equal(ba, bb) and bits_equal(la, lb)
     assert np.array_equal(a.resampled_times(), b.resampled_times())
     assert 0.05 < sa.mean() < 0.98
+
+
+def test_block_larger_than_the_grid_raises_like_the_reference():
+    """A block cut by both edges makes the reference's slices differ in length (numpy broadcast ValueError)."""
+    from mcmc_gpu_b200 import MCMC
+    case = dict(TRAJECTORY_CASES["ragged_rf"])
+    case["blocks"] = (60, 100, 12, 26)               # wider than the 90-column grid
+    ch, rf, g = product_chain(case)
+    with pytest.raises(ValueError, match="broadcast"):
+        MCMC.ChainBatch(ch, rf, g["bed0"][None], [1])
