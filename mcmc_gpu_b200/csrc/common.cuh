@@ -139,10 +139,12 @@ struct gmc_ctx {
     double field_res;      // grid spacing of the proposal fields (gmc_set_blocks)
     int64_t launches;
     long long* d_phase;    // optional per-phase cycle counters of run_kernel (debug)
-    int* d_sched;          // run_kernel work counter + per-chain completed-chunk counts (launches with C > resident CTAs)
+    int* d_sched;          // GMC_SCHED_SLOTS areas of [work counter, completed chunks per chain] (launches with C > resident CTAs)
+    unsigned sched_next;
     gmc_sgs_state* sgs;    // small-scale (SGS) chain tables, see sgs.cu
 };
 
+#define GMC_SCHED_SLOTS 16
 #define FLAG_GATE 1
 #define FLAG_MC 2
 

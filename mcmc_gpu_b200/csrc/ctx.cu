@@ -67,6 +67,7 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->launches = 0;
     c->d_phase = nullptr;
     c->d_sched = nullptr;
+    c->sched_next = 0;
     c->sgs = nullptr;
     c->dev.H = H;
     c->dev.W = W;

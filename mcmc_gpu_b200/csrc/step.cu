@@ -1404,9 +1404,12 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
     int grid = C, chunk = n_steps;
     int* sched = nullptr;
     if (C > slots && vec && n_steps > 1 && !getenv("GMC_STATIC_SCHED")) {
-        if (!c->d_sched) GMC_CUDA(cudaMalloc(&c->d_sched, (size_t)(c->max_chains + 1) * sizeof(int)));
-        GMC_CUDA(cudaMemsetAsync(c->d_sched, 0, (size_t)(C + 1) * sizeof(int), (cudaStream_t)stream));
-        sched = c->d_sched;
+        // launches for disjoint chain ranges may run concurrently on different streams (run_pipelined): each takes the
+        // next of GMC_SCHED_SLOTS scheduler areas
+        const size_t area = (size_t)c->max_chains + 1;
+        if (!c->d_sched) GMC_CUDA(cudaMalloc(&c->d_sched, GMC_SCHED_SLOTS * area * sizeof(int)));
+        sched = c->d_sched + (size_t)(c->sched_next++ % GMC_SCHED_SLOTS) * area;
+        GMC_CUDA(cudaMemsetAsync(sched, 0, (size_t)(C + 1) * sizeof(int), (cudaStream_t)stream));
         grid = slots;
         chunk = std::max(4, (n_steps + 31) / 32);
     }

@@ -201,3 +201,31 @@ def test_block_larger_than_the_grid_raises_like_the_reference():
     ch, rf, g = product_chain(case)
     with pytest.raises(ValueError, match="broadcast"):
         MCMC.ChainBatch(ch, rf, g["bed0"][None], [1])
+
+
+def test_concurrent_chunk_scheduled_launches_do_not_share_scheduler_state(monkeypatch):
+    """run_pipelined issues one launch per chain range on its own stream; with more chains per range than resident CTAs
+    every launch is chunk-scheduled and they run concurrently - each must use its own scheduler area."""
+    import torch
+    from mcmc_gpu_b200 import MCMC
+    case = dict(TRAJECTORY_CASES["ragged_rf"])
+    ch, rf, g = product_chain(case)
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    C, n_iter = 3 * (2 * sm + 9), 19                          # three ranges, each above the CTA slots
+    beds0 = np.stack([g["bed0"] + 0.01 * (k % 13) for k in range(C)])
+    seeds = list(range(700, 700 + C))
+    keys = [MCMC.philox_key(s, s) for s in seeds]
+    host = torch.as_tensor(beds0).pin_memory()
+    out = {"bed": torch.empty((C,) + g["bed0"].shape, dtype=torch.float64).pin_memory(),
+           "loss": torch.empty((C, n_iter), dtype=torch.float64).pin_memory(),
+           "steps": torch.empty((C, n_iter), dtype=torch.uint8).pin_memory(),
+           "blocks": torch.empty((C, n_iter, 4), dtype=torch.int32).pin_memory()}
+    batch = MCMC.ChainBatch(ch, rf, host, keys)
+    res = batch.run_pipelined(host, keys, n_iter - 1, out, groups=3)
+    piped = {k: v.numpy().copy() for k, v in res.items()}
+    monkeypatch.setenv("GMC_STATIC_SCHED", "1")
+    ref = MCMC.ChainBatch(ch, rf, beds0, keys)
+    lr, sr, br = ref.advance(n_iter - 1)
+    assert bits_equal(piped["bed"], ref.beds())
+    assert np.array_equal(piped["steps"][:, 1:], sr) and np.array_equal(piped["blocks"][:, 1:], br)
+    assert bits_equal(piped["loss"][:, 1:], lr)
