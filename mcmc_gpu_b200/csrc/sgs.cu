@@ -1104,7 +1104,7 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
         sched = c->d_sched + (size_t)(c->sched_next++ % GMC_SCHED_SLOTS) * area;
         GMC_CUDA(cudaMemsetAsync(sched, 0, (size_t)(C + 1) * sizeof(int), (cudaStream_t)stream));
         grid = slots;
-        chunk = std::max(2, (n_steps + 31) / 32);
+        chunk = std::min(256, std::max(2, (n_steps + 31) / 32));   // see gmc_run (step.cu)
     }
     if (c->sgs->warp_solver)
         sgs_run_kernel<true><<<grid, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(

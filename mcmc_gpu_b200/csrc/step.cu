@@ -1411,7 +1411,9 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
         sched = c->d_sched + (size_t)(c->sched_next++ % GMC_SCHED_SLOTS) * area;
         GMC_CUDA(cudaMemsetAsync(sched, 0, (size_t)(C + 1) * sizeof(int), (cudaStream_t)stream));
         grid = slots;
-        chunk = std::max(4, (n_steps + 31) / 32);
+        // ~32 chunks per chain, at most 256 iterations each: short chunks keep the tail small and the waits on a
+        // predecessor chunk (bounded spin in the kernel) in the millisecond range however long the launch is
+        chunk = std::min(256, std::max(4, (n_steps + 31) / 32));
     }
     run_kernel<<<grid, GMC_STEP_THREADS, c->step_smem_bytes, (cudaStream_t)stream>>>(
         c->dev, bed, mcres, ssq, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride, cache_offset, resampled,
