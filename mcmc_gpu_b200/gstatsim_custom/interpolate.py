@@ -54,6 +54,23 @@ def _sanity_checks(xx, yy, grid, vario, radius, num_points, ktype, sim_mask):
         raise ValueError("ktype must be 'ok' or 'sk'")
 
 
+def search_levels(dx, dy, H, W, radius):
+    """Octant search tables for `radius` and its widened versions: a node that finds no data within `radius` searches
+    again with radius + 100 km (interpolate.py:149-155).  The octant lists are sorted by distance, so every radius level is
+    a prefix of the lists built for the widest one; levels stop once the radius covers the grid diagonal (or after
+    MAX_LEVELS, or when the tables would get unreasonably large).
+    Returns (offsets int16 [8, lmax, 2], counts int32 [levels, 8], half-width of the widest window, radii)."""
+    diag = float(np.hypot(abs(dx) * W, abs(dy) * H))
+    radii = [float(radius)]
+    while radii[-1] < diag and len(radii) < MAX_LEVELS and (radii[-1] + 100e3) / min(abs(dx), abs(dy)) <= MAX_HALF_WIDTH:
+        radii.append(radii[-1] + 100e3)
+    off, cnt_max, hw = octant_stencil(dx, dy, radii[-1])
+    dist = np.sqrt((off[..., 1] * dx) ** 2 + (off[..., 0] * dy) ** 2)         # [8, lmax], the reference's expression
+    valid = np.arange(off.shape[1])[None, :] < cnt_max[:, None]
+    cnt = np.stack([((dist < r) & valid).sum(1) for r in radii]).astype(np.int32)   # [levels, 8]
+    return off, cnt, hw, radii
+
+
 def sgs_many(xx, yy, grid, variogram, seeds, radius=100e3, num_points=20, ktype="ok", sim_mask=None, bounds=None,
              n_quantiles=500, nst_tables=None, as_tensor=False):
     """Realisations for every seed in `seeds` (ints or numpy Generators), stacked [len(seeds), H, W].
@@ -141,17 +158,7 @@ def sgs_many(xx, yy, grid, variogram, seeds, radius=100e3, num_points=20, ktype=
     path_d, ord_d, noise_d = cu(paths, torch.int32), cu(ords, torch.int32), cu(noise)
 
     dx, dy = grid_steps(xx, yy)
-    # A node that finds no data within `radius` searches again with radius + 100 km (interpolate.py:149-155).  The octant
-    # lists are sorted by distance, so every radius level is a prefix of the lists built for the widest one; levels stop
-    # once the radius covers the grid diagonal (or after MAX_LEVELS, or when the tables would get unreasonably large).
-    diag = float(np.hypot(abs(dx) * W, abs(dy) * H))
-    radii = [float(radius)]
-    while radii[-1] < diag and len(radii) < MAX_LEVELS and (radii[-1] + 100e3) / min(abs(dx), abs(dy)) <= MAX_HALF_WIDTH:
-        radii.append(radii[-1] + 100e3)
-    off, cnt_max, hw = octant_stencil(dx, dy, radii[-1])
-    dist = np.sqrt((off[..., 1] * dx) ** 2 + (off[..., 0] * dy) ** 2)         # [8, lmax], the reference's expression
-    valid = np.arange(off.shape[1])[None, :] < cnt_max[:, None]
-    cnt = np.stack([((dist < r) & valid).sum(1) for r in radii]).astype(np.int32)   # [levels, 8]
+    off, cnt, hw, radii = search_levels(dx, dy, H, W, radius)
     vario = {k: (v.lower() if k == "vtype" else float(v)) for k, v in variogram.items()}
     lut = covariance_lut(dx, dy, hw, vario)
     off_d, cnt_d, lut_d = cu(off, torch.int16), cu(cnt, torch.int32), cu(lut)

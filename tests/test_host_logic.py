@@ -151,3 +151,16 @@ def test_whole_grid_sgs_argument_checks_and_no_cpu_fallback():
     if not torch.cuda.is_available():
         with pytest.raises(GmcError, match="no CPU fallback"):
             interpolate.sgs(xx, yy, grid, vario, radius=500.0, num_points=8, seed=1)
+
+
+def test_whole_grid_sgs_search_levels_are_prefixes_of_the_widest_lists():
+    from mcmc_gpu_b200.gstatsim_custom.interpolate import search_levels
+    from mcmc_gpu_b200.sgs_tables import octant_stencil
+    off, cnt, hw, radii = search_levels(500.0, 500.0, 120, 150, 3e3)
+    assert radii == [3e3, 103e3] and cnt.shape == (2, 8) and (cnt[1] >= cnt[0]).all()
+    off0, cnt0, hw0 = octant_stencil(500.0, 500.0, 3e3)
+    assert np.array_equal(cnt[0], cnt0)                                  # level 0 is exactly the search for `radius`
+    for o in range(8):
+        assert np.array_equal(off[o, :cnt0[o]], off0[o, :cnt0[o]])       # ... and its offsets are a prefix of the wide lists
+    # a radius that already covers the grid needs no second level
+    assert len(search_levels(500.0, 500.0, 20, 20, 50e3)[3]) == 1
