@@ -257,6 +257,18 @@ GMC_API int64_t gmc_launch_count(const gmc_ctx* ctx);
 /* Dynamic shared memory (bytes) and threads per CTA of the fused step kernel for the current block table. */
 GMC_API int gmc_step_kernel_info(const gmc_ctx* ctx, int* smem_bytes, int* threads, int* ctas_per_sm);
 
+/* Reports - then clears - the device-error flag (synchronize != 0: after waiting for the device; 0: as stored by the
+ * launches that have finished, for callers that synchronised their own streams): GMC_ECUDA when a kernel of an earlier launch
+ * gave up one of its bounded in-kernel waits (a (chunk, chain) item waiting for its chain's previous chunk, or a tile copy
+ * that never completed) instead of running on with stale state; gmc_run / gmc_sgs_run also refuse to start while the flag
+ * is set.  The reference has no counterpart (its chains are OS processes, largeScaleChain_multiprocessing.py:78-79); this
+ * is the error path of the (chunk, chain) scheduler that replaces them. */
+GMC_API int gmc_check(gmc_ctx* ctx, int synchronize);
+
+/* Measures the FP64 FMA rate of the device with a register-resident DFMA loop (TFLOP/s, 2 flops per FMA): the
+ * denominator of the FP64-pipe fractions quoted for the step and kriging kernels. */
+GMC_API int gmc_debug_fp64_peak(gmc_ctx* ctx, double* tflops_out);
+
 /* Debug: per-phase SM-cycle accounting of the fused step kernel (thread 0 of every CTA, summed over CTAs and steps).
  * enable != 0 allocates/zeroes the counters, 0 releases them; cycles_out (host, 8 x int64, may be NULL) receives the
  * counters accumulated so far: 0 scalars+prefetch, 1 spectrum fill, 2 column DFT, 3 row recombination, 4 row DFT,

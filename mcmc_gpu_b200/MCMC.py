@@ -85,6 +85,21 @@ class RandField:
         self._draws = 0          # Philox iteration counter of stand-alone get_rfblock() calls
         self._ctx = None
 
+    def _config_key(self):
+        """Hashable digest of everything a device context derives from this object (model, ranges, block table, tapers)."""
+        import hashlib
+        h = hashlib.blake2b(digest_size=16)
+        pairs = getattr(self, "pairs", None)
+        if pairs is not None:
+            h.update(np.ascontiguousarray(pairs, dtype=np.int64).tobytes())
+        for m in getattr(self, "edge_masks", None) or []:
+            a = np.ascontiguousarray(m, dtype=np.float64)
+            h.update(repr(a.shape).encode())
+            h.update(a.tobytes())
+        return (self.model_name, self.smoothness, bool(self.isotropic), self.range_min_x, self.range_max_x, self.range_min_y,
+                self.range_max_y, self.scale_min, self.scale_max, self.nugget_max, getattr(self, "resolution", None),
+                h.hexdigest())
+
     def set_generation_method(self, spectral, n_modes=1000):
         """True: FFT spectral synthesis (A3).  False: the gstools randomization method of `get_random_field`
         (MCMC.py:625-687) with `n_modes` wave vectors (gstools SRF default mode_no=1000), generated on the GPU."""
@@ -139,16 +154,12 @@ class RandField:
 
     def get_crf_weight(self, xx, yy, cond_data_mask):
         """(weight, dist, dist_rescale, dist_logi): conditioning weight, 0 at data cells (MCMC.py:689-714).
-        One-time setup, outside the hot path; the nearest-data distance is an exact scan on the GPU (Utilities.py)."""
+        One-time setup, outside the hot path; the nearest-data distance is an exact scan on the GPU (Utilities.py,
+        bit-identical to the reference's KD-tree query).  No CPU fallback: without a CUDA device this raises GmcError; a
+        host that only prepares inputs can compute the distance map itself and call get_crf_weight_from_dist."""
         sel = np.asarray(cond_data_mask) == 1
-        import torch
-        if torch.cuda.is_available():
-            from .Utilities import min_dist_from_mask            # exact GPU scan, bit-identical to the KD-tree query
-            dist = min_dist_from_mask(np.asarray(xx), np.asarray(yy), sel)
-        else:                                                    # setup on a GPU-less host (e.g. preparing inputs)
-            from scipy.spatial import cKDTree
-            tree = cKDTree(np.column_stack([xx[sel], yy[sel]]))
-            dist = tree.query(np.column_stack([xx.ravel(), yy.ravel()]))[0].reshape(xx.shape)
+        from .Utilities import min_dist_from_mask
+        dist = min_dist_from_mask(np.asarray(xx), np.asarray(yy), sel)
         return self.get_crf_weight_from_dist(xx, yy, dist)
 
     def get_crf_weight_from_dist(self, xx, yy, dist):
@@ -348,7 +359,9 @@ class chain:
                     centre_cells=centre, crf_weight=weight, resolution=self.resolution, sigma_mc=self.sigma_mc)
 
     def _context(self, max_chains=1, RF=None, device=None):
-        key = (max_chains, id(RF), str(device))
+        # the cached context holds the field model, block table and tapers: key it on the RandField's CONTENTS (a setter
+        # call on RF, or a re-created RF that happens to reuse the id, must not leave the old configuration in place)
+        key = (max_chains, None if RF is None else RF._config_key(), str(device))
         if self._ctx is None or self._ctx_key != key:
             H, W = self.xx.shape
             ctx = Context(H, W, max_chains, device)
@@ -477,47 +490,61 @@ class chain_crf(chain):
         return out + ((sample_values,) if sample_values is not None else ())
 
     def run_many(self, n_iter, RF, initial_beds, rng_seeds, device=None, resync_every=4096, track_resampled=True,
-                 as_arrays=False, batch=None, out=None, pipeline_groups=None):
+                 as_arrays=False, batch=None, out=None, pipeline_groups=None, wait=True):
         """Batched form: C independent chains (one per initial bed / seed) stepped concurrently on one GPU.
 
         Returns a list of the reference's 7-tuples (only_save_last_bed=True form), one per chain — what
         largeScaleChain_mp collects from its worker processes (largeScaleChain_multiprocessing.py:78-79) — or, with
-        as_arrays=True, a dict of stacked arrays (bed[C,H,W], loss[C,n], steps[C,n], blocks[C,n,4], resampled_times).
+        as_arrays=True, a dict of stacked arrays (bed[C,H,W], loss[C,n], steps[C,n], blocks[C,n,4], resampled[C,H,W]).
         initial_beds: numpy [C,H,W] or a (pinned) CPU / CUDA torch tensor.  `batch` reuses the device buffers of a
-        previous call; `out` = dict of pinned CPU tensors (bed, loss, steps, blocks) to receive the results.
+        previous call (and stays open: only a batch created here is closed here); `out` = dict of pinned CPU tensors
+        (bed, loss, steps, blocks and optionally resampled: int32 coverage counts) to receive the results.
+        wait=False (pinned beds + batch + out, as_arrays=True): the uploads, kernels and downloads are only queued and a
+        PendingRun is returned; its wait() blocks until the results are in `out`.  Two batches used alternately keep two
+        steps in flight, so the transfers of one overlap the compute of the other.
         """
         if not isinstance(RF, RandField):
             raise TypeError('The arugment "RF" has to be an object of the class RandField')
         keys = [philox_key(s, s) for s in rng_seeds]
         import torch
-        if (batch is not None and out is not None and isinstance(initial_beds, torch.Tensor) and initial_beds.is_pinned()
-                and (pipeline_groups is None or pipeline_groups > 1)):
+        pipelined = (batch is not None and out is not None and isinstance(initial_beds, torch.Tensor) and initial_beds.is_pinned()
+                     and (pipeline_groups is None or pipeline_groups > 1))
+        if not wait and not (pipelined and as_arrays):
+            raise ValueError("wait=False needs pinned initial beds, a reusable batch, pinned `out` tensors and as_arrays=True")
+        own_batch = batch is None
+        if pipelined:
             # pinned host buffers on both sides: overlap the transfers with compute
             if pipeline_groups is None:
                 # finer ranges shorten the exposed head (first upload) and tail (last download) of the pipeline:
                 # 4 ranges 50.5 ms, 8: 49.6 ms, 16: 49.1 ms per 256 x 1000-iteration step (profiles/README.md)
                 pipeline_groups = int(os.environ.get("GMC_PIPELINE_GROUPS", "16"))
-            res = batch.run_pipelined(initial_beds, keys, n_iter - 1, out, groups=pipeline_groups, resync_every=resync_every)
-            if as_arrays:
-                res["batch"] = batch
-                return res
-        if batch is None:
-            batch = ChainBatch(self, RF, initial_beds, keys, iter0=1, device=device, track_resampled=track_resampled)
-        else:
-            batch.reset(initial_beds, keys, iter0=1)
-        C = batch.C
-        res = batch.advance_into(n_iter - 1, resync_every=resync_every, out=out)
-        if as_arrays:
+            pending = batch.run_pipelined(initial_beds, keys, n_iter - 1, out, groups=pipeline_groups, resync_every=resync_every,
+                                          wait=False)
+            if not wait:
+                return pending
+            res = pending.wait()
             res["batch"] = batch
+        else:
+            if batch is None:
+                batch = ChainBatch(self, RF, initial_beds, keys, iter0=1, device=device, track_resampled=track_resampled)
+            else:
+                batch.reset(initial_beds, keys, iter0=1)
+            res = batch.advance_into(n_iter - 1, resync_every=resync_every, out=out)
+            res["batch"] = batch
+        if as_arrays:
             return res
+        C = batch.C
         final, lc, st, bl = res["bed"], res["loss"], res["steps"], res["blocks"]
-        res_t = batch.resampled_times() if track_resampled else [np.zeros((batch.H, batch.W))] * C
+        res_t = batch.resampled_times() if batch.resampled is not None else [np.zeros((batch.H, batch.W))] * C
         outl = []
         for c in range(C):
             loss = np.array(lc[c], dtype=np.float64)
+            blocks = np.array(bl[c], dtype=np.float64)
+            blocks[0, :] = np.nan                     # MCMC.py:1169: row 0 of blocks_cache stays NaN
             outl.append((np.array(final[c]), loss.copy(), np.zeros(n_iter), loss, np.array(st[c], dtype=np.float64), res_t[c],
-                         np.array(bl[c], dtype=np.float64)))
-        batch.close()
+                         blocks))
+        if own_batch:
+            batch.close()
         return outl
 
 
@@ -762,6 +789,32 @@ class SgsBatch:
         return acc.cpu().numpy().astype(bool), loss.cpu().numpy()
 
 
+class PendingRun:
+    """Handle of a queued ChainBatch.run_pipelined: wait() blocks until every range's results are in the pinned `out`
+    tensors, checks the device-error flag and returns `out`.  The batch must not be reused before wait() returns."""
+
+    def __init__(self, batch, out):
+        self.batch, self.out = batch, out
+        torch = batch.torch
+        self._events = []
+        for strm in batch._streams:
+            ev = torch.cuda.Event()
+            ev.record(strm)
+            self._events.append(ev)
+        self._done = False
+
+    def wait(self):
+        if not self._done:
+            for ev in self._events:
+                ev.synchronize()
+            main = self.batch.torch.cuda.current_stream()
+            for strm in self.batch._streams:
+                main.wait_stream(strm)
+            self.batch.ctx.check_flag()
+            self._done = True
+        return dict(self.out)
+
+
 class ChainBatch:
     """Device-resident state of C chains sharing one chain_crf configuration: bed[C,H,W], mcres[C,H,W], ssq[C]."""
 
@@ -842,7 +895,9 @@ class ChainBatch:
         self.iteration += n_steps
         if not want_caches:
             return None
-        return lc.cpu().numpy(), st.cpu().numpy(), bl.cpu().numpy()
+        res = lc.cpu().numpy(), st.cpu().numpy(), bl.cpu().numpy()
+        self.ctx.check_flag()
+        return res
 
     def advance_into(self, n_steps, resync_every=4096, out=None):
         """The reference's per-chain outputs for a run of n_steps+1 iterations (index 0 = initial state, MCMC.py:1193-1199)
@@ -861,27 +916,31 @@ class ChainBatch:
             out["loss"].copy_(lc, non_blocking=True)
             out["steps"].copy_(st, non_blocking=True)
             out["blocks"].copy_(bl, non_blocking=True)
+            if "resampled" in out and self.resampled is not None:
+                out["resampled"].copy_(self.resampled, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+            self.ctx.check_flag()
             return dict(out)
         blocks = bl.cpu().numpy().astype(np.float64)
         blocks[:, 0, :] = np.nan                      # MCMC.py:1169: row 0 of blocks_cache stays NaN
         return dict(bed=self.bed.cpu().numpy(), loss=lc.cpu().numpy(), steps=st.cpu().numpy(), blocks=blocks)
 
-    def run_pipelined(self, host_beds, keys, n_steps, out, groups=4, iter0=1, resync_every=4096):
+    def run_pipelined(self, host_beds, keys, n_steps, out, groups=4, iter0=1, resync_every=4096, wait=True):
         """End-to-end run with host<->device transfers overlapped with compute: the chains are split into `groups` ranges,
         each on its own CUDA stream (H2D of the beds -> residual+loss -> n_steps fused iterations -> D2H of the results).
         The ranges start staggered by their H2D copies, so the D2H of one range overlaps the compute of the others.
-        host_beds / out[...] are pinned CPU tensors; results are identical to `reset` + `advance_into` (chains are
-        independent and counter-addressed)."""
+        host_beds / out[...] are pinned CPU tensors (out may hold "resampled": int32 [C,H,W]); results are identical to
+        `reset` + `advance_into` (chains are independent and counter-addressed).  wait=False returns a PendingRun as soon
+        as the work is queued (one cudaMemcpyAsync per buffer and range; nothing batched)."""
         torch = self.torch
         if tuple(host_beds.shape) != (self.C, self.H, self.W) or host_beds.dtype != torch.float64:
             raise GmcShapeError(f"initial beds must be float64 [{self.C},{self.H},{self.W}]")
+        if "resampled" in out and self.resampled is None:
+            raise GmcError("out['resampled'] given but the ChainBatch was created with track_resampled=False")
         n = n_steps + 1
         lc, st, bl = self._device_caches(n)
         self.seeds = keys_tensor(keys, self.dev)
         den = torch.full((1,), 2 * self.chain.sigma_mc ** 2, dtype=torch.float64, device=self.dev)
-        if self.resampled is not None:
-            self.resampled.zero_()
         groups = max(1, min(int(groups), self.C))
         if not hasattr(self, "_streams") or len(self._streams) != groups:
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(groups)]
@@ -894,6 +953,8 @@ class ChainBatch:
             strm.wait_stream(main)
             with torch.cuda.stream(strm):
                 self.bed[a:b].copy_(host_beds[a:b], non_blocking=True)
+                if self.resampled is not None:
+                    self.resampled[a:b].zero_()
                 self.ctx.residual_loss_range(self.bed[a:b], self.mcres[a:b], self._loss[a:b], self.ssq[a:b], a)
                 lc[a:b, 0] = self.ssq[a:b] / den
                 st[a:b, 0] = 0
@@ -904,11 +965,11 @@ class ChainBatch:
                 out["loss"][a:b].copy_(lc[a:b], non_blocking=True)
                 out["steps"][a:b].copy_(st[a:b], non_blocking=True)
                 out["blocks"][a:b].copy_(bl[a:b], non_blocking=True)
-        for strm in self._streams:
-            main.wait_stream(strm)
-        main.synchronize()
+                if "resampled" in out:
+                    out["resampled"][a:b].copy_(self.resampled[a:b], non_blocking=True)
         self.iteration = int(iter0) + n_steps
-        return dict(out)
+        pending = PendingRun(self, out)
+        return pending.wait() if wait else pending
 
     def step_injected(self, fields, centres, us):
         """One step per chain with injected proposals.  Returns (accepted[C] bool, loss[C])."""

@@ -64,6 +64,8 @@ PROTOTYPES = {
     "gmc_mode_filter_binary": (C.c_int, [C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int, _c_p]),
     "gmc_launch_count": (_i64, [_c_p]),
     "gmc_step_kernel_info": (C.c_int, [_c_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gmc_check": (C.c_int, [_c_p, C.c_int]),
+    "gmc_debug_fp64_peak": (C.c_int, [_c_p, C.POINTER(_f64)]),
     "gmc_debug_phase_timing": (C.c_int, [_c_p, C.c_int, _c_p]),
     "gmc_debug_div_check": (C.c_int, [_c_p, _c_p, _i64, _f64, C.POINTER(_i64)]),
 }
@@ -310,7 +312,39 @@ class Context:
         check(self.lib.gmc_debug_div_check(self._h, _ptr(x), x.numel(), float(divisor), C.byref(n)))
         return int(n.value)
 
-    def step_kernel_info(self):
+    def step_kernel_info(self, n_chains=None):
+        """Launch shape of the fused step kernel; with n_chains, the CTA size gmc_run picks for that many chains (512
+        threads, one CTA per SM, when there are no more chains than SMs; else 256 threads, two CTAs per SM)."""
         a, b, c = C.c_int(), C.c_int(), C.c_int()
         check(self.lib.gmc_step_kernel_info(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        return dict(smem_bytes=a.value, threads=b.value, ctas_per_sm=c.value)
+        info = dict(smem_bytes=a.value, threads=b.value, ctas_per_sm=c.value)
+        if n_chains is not None:
+            import torch
+            sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+            wide = n_chains <= sms
+            env = os.environ.get("GMC_STEP_WIDE")
+            if env is not None:
+                wide = env[:1] == "1" and n_chains <= c.value * sms
+            if wide:
+                info.update(threads=512, ctas_per_sm=1)
+        return info
+
+    def check(self):
+        """Synchronise and raise GmcError if a kernel gave up a bounded in-kernel wait (chain state of that launch invalid)."""
+        check(self.lib.gmc_check(self._h, 1))
+
+    def check_flag(self):
+        """The same without synchronising: for callers that have just waited for the streams / copies they queued."""
+        check(self.lib.gmc_check(self._h, 0))
+
+    def fp64_peak_tflops(self) -> float:
+        """Measured FP64 FMA rate of this GPU (register-resident DFMA loop), TFLOP/s."""
+        v = _f64(0.0)
+        check(self.lib.gmc_debug_fp64_peak(self._h, C.byref(v)))
+        return float(v.value)
+
+    def stencil_kernel_name(self) -> str:
+        """Which full-grid stencil kernel gmc_residual / gmc_residual_loss launch for this grid."""
+        if self.W % 2 == 0 and not os.environ.get("GMC_RS_LEGACY"):
+            return "residual_tma_kernel (TMA tensor tiles on an mbarrier ring)"
+        return "residual_kernel (cp.async ring; odd W or GMC_RS_LEGACY)"

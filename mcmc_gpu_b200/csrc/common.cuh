@@ -141,10 +141,25 @@ struct gmc_ctx {
     long long* d_phase;    // optional per-phase cycle counters of run_kernel (debug)
     int* d_sched;          // GMC_SCHED_SLOTS areas of [work counter, completed chunks per chain] (launches with C > resident CTAs)
     unsigned sched_next;
+    cudaEvent_t sched_ev[16];   // recorded behind the launch that used the area: the next user waits for it on ITS stream
+    bool sched_used[16];
+    int sched_cur;         // area handed out by the last gmc_sched_acquire
+    int* h_err;            // pinned + mapped: a kernel that gives up a bounded wait stores a GMC_DEVERR_* code here
+    int* d_err;            // device alias of h_err
+    unsigned spin_limit;   // bound of the in-kernel waits (GMC_DEBUG_SPIN_LIMIT overrides the default 2^26)
+    int step_wide_ctas;    // occupancy of the 512-thread step kernel (0 = unavailable)
     gmc_sgs_state* sgs;    // small-scale (SGS) chain tables, see sgs.cu
 };
 
 #define GMC_SCHED_SLOTS 16
+#define GMC_DEVERR_WAIT_TIMEOUT 1   // a chunk gave up waiting for its chain's previous chunk (or a tile copy never completed)
+
+// scheduler areas for launches with more chains than resident CTAs (ctx.cu): acquire zeroes an area on `st` after making the
+// stream wait for the area's previous user; release records that user's completion.  check_device_error reads the mapped
+// flag without synchronising (it reports what earlier, already finished launches stored).
+int gmc_sched_acquire(struct gmc_ctx* c, int C, cudaStream_t st, int** sched_out);
+void gmc_sched_release(struct gmc_ctx* c, cudaStream_t st);
+int gmc_check_device_error(struct gmc_ctx* c, const char* who);
 #define FLAG_GATE 1
 #define FLAG_MC 2
 

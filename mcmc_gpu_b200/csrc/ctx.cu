@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include <cstdlib>
 
 static thread_local char g_err[512] = "";
 
@@ -68,6 +69,22 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->d_phase = nullptr;
     c->d_sched = nullptr;
     c->sched_next = 0;
+    c->sched_cur = -1;
+    for (int k = 0; k < GMC_SCHED_SLOTS; ++k) {
+        c->sched_ev[k] = nullptr;
+        c->sched_used[k] = false;
+    }
+    c->h_err = c->d_err = nullptr;
+    c->step_wide_ctas = 0;
+    c->spin_limit = 1u << 26;
+    if (const char* e = getenv("GMC_DEBUG_SPIN_LIMIT")) c->spin_limit = (unsigned)strtoul(e, nullptr, 10);
+    if (cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&c->d_err, c->h_err, 0) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        GMC_FAIL(GMC_ECUDA, "gmc_create: cannot allocate the mapped device-error flag");
+    }
+    *c->h_err = 0;
     c->sgs = nullptr;
     c->dev.H = H;
     c->dev.W = W;
@@ -92,6 +109,9 @@ extern "C" int gmc_destroy(gmc_ctx* c) {
     cudaFree(c->d_edge_masks);
     cudaFree(c->d_phase);
     cudaFree(c->d_sched);
+    for (int k = 0; k < GMC_SCHED_SLOTS; ++k)
+        if (c->sched_ev[k]) cudaEventDestroy(c->sched_ev[k]);
+    if (c->h_err) cudaFreeHost(c->h_err);
     gmc_sgs_destroy(c);
     delete c;
     return GMC_OK;
@@ -361,6 +381,91 @@ extern "C" int gmc_set_blocks(gmc_ctx* c, int n_pairs, const int32_t* pair_w, co
 }
 
 extern "C" int64_t gmc_launch_count(const gmc_ctx* c) { return c ? c->launches : 0; }
+
+int gmc_sched_acquire(gmc_ctx* c, int C, cudaStream_t st, int** sched_out) {
+    const size_t area = (size_t)c->max_chains + 1;
+    if (!c->d_sched) GMC_CUDA(cudaMalloc(&c->d_sched, GMC_SCHED_SLOTS * area * sizeof(int)));
+    const int k = (int)(c->sched_next++ % GMC_SCHED_SLOTS);
+    if (!c->sched_ev[k]) GMC_CUDA(cudaEventCreateWithFlags(&c->sched_ev[k], cudaEventDisableTiming));
+    // more than GMC_SCHED_SLOTS scheduled launches in flight: this one queues behind the area's previous user
+    if (c->sched_used[k]) GMC_CUDA(cudaStreamWaitEvent(st, c->sched_ev[k], 0));
+    int* sched = c->d_sched + (size_t)k * area;
+    GMC_CUDA(cudaMemsetAsync(sched, 0, (size_t)(C + 1) * sizeof(int), st));
+    c->sched_cur = k;
+    *sched_out = sched;
+    return GMC_OK;
+}
+
+void gmc_sched_release(gmc_ctx* c, cudaStream_t st) {
+    if (c->sched_cur < 0) return;
+    cudaEventRecord(c->sched_ev[c->sched_cur], st);
+    c->sched_used[c->sched_cur] = true;
+    c->sched_cur = -1;
+}
+
+int gmc_check_device_error(gmc_ctx* c, const char* who) {
+    const int code = *(volatile int*)c->h_err;
+    if (code == 0) return GMC_OK;
+    *c->h_err = 0;
+    GMC_FAIL(GMC_ECUDA, "%s: a kernel gave up a bounded in-kernel wait (device error %d: a chunk's predecessor or a tile copy did not "
+             "complete within the spin limit, e.g. under a debugger or on a shared GPU); the chain state of that launch is invalid", who, code);
+}
+
+// Register-resident DFMA loop: the FP64 FMA rate this GPU sustains (8 independent chains per thread, 32 warps per SM), the
+// denominator for the FP64-pipe fractions quoted for the step and kriging kernels.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double b, double c0) {
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-3 * (threadIdx.x + 32 * k);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c0);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int gmc_debug_fp64_peak(gmc_ctx* c, double* tflops_out) {
+    if (!c || !tflops_out) GMC_FAIL(GMC_EINVAL, "gmc_debug_fp64_peak: NULL argument");
+    GMC_CUDA(cudaSetDevice(c->device));
+    const int ctas = c->sm_count * 4, iters = 4096;
+    double* d = nullptr;
+    GMC_CUDA(cudaMalloc(&d, (size_t)ctas * 256 * sizeof(double)));
+    cudaEvent_t e0, e1;
+    GMC_CUDA(cudaEventCreate(&e0));
+    GMC_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {          // first pass warms up; best of the rest
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<ctas, 256>>>(d, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1);
+        GMC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    GMC_CUDA(cudaGetLastError());
+    *tflops_out = 2.0 * 8.0 * 4.0 * iters * (double)ctas * 256.0 / (best * 1e-3) / 1e12;
+    return GMC_OK;
+}
+
+// Reports (then clears) the device-error flag; synchronize != 0 waits for the device first, 0 reads what finished launches
+// stored (for callers that have synchronised the streams they care about themselves).
+extern "C" int gmc_check(gmc_ctx* c, int synchronize) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_check: ctx is NULL");
+    if (synchronize) {
+        GMC_CUDA(cudaSetDevice(c->device));
+        GMC_CUDA(cudaDeviceSynchronize());
+    }
+    return gmc_check_device_error(c, "gmc_check");
+}
 
 extern "C" int gmc_step_kernel_info(const gmc_ctx* c, int* smem_bytes, int* threads, int* ctas_per_sm) {
     if (!c) GMC_FAIL(GMC_EINVAL, "gmc_step_kernel_info: ctx is NULL");

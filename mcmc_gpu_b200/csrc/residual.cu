@@ -405,16 +405,27 @@ __global__ void __launch_bounds__(LOSS_THREADS)
     if (threadIdx.x == 0) partials[(int64_t)c * n_tiles + blockIdx.x] = t;
 }
 
-// fixed-order sum of the per-tile partials: one warp per chain
-__global__ void finalize_loss_kernel(const double* __restrict__ partials, int n_tiles, double two_sigma2,
-                                     double* __restrict__ loss_out, double* __restrict__ ssq_out, int C) {
-    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (c >= C) return;
-    const int lane = threadIdx.x & 31;
-    double acc = 0.0;
-    for (int k = lane; k < n_tiles; k += 32) acc += partials[(int64_t)c * n_tiles + k];
-    acc = warp_sum(acc);
-    if (lane == 0) {
+// fixed-order sum of the per-tile partials: one CTA per chain (thread-strided sums, then the block tree).  One warp per chain
+// took 45 us for 256 x 2016 partials - a quarter of the fused residual+loss time at 500x500 - because 32 CTAs of dependent
+// adds cannot hide the load latency.
+#define FIN_THREADS 256
+__global__ void __launch_bounds__(FIN_THREADS)
+    finalize_loss_kernel(const double* __restrict__ partials, int n_tiles, double two_sigma2, double* __restrict__ loss_out,
+                         double* __restrict__ ssq_out, int C) {
+    __shared__ double scratch[33];
+    const int c = blockIdx.x;
+    const double* p = partials + (int64_t)c * n_tiles;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int k = threadIdx.x;
+    for (; k + 3 * FIN_THREADS < n_tiles; k += 4 * FIN_THREADS) {      // four loads in flight per thread
+        a0 += p[k];
+        a1 += p[k + FIN_THREADS];
+        a2 += p[k + 2 * FIN_THREADS];
+        a3 += p[k + 3 * FIN_THREADS];
+    }
+    for (; k < n_tiles; k += FIN_THREADS) a0 += p[k];
+    const double acc = block_sum<FIN_THREADS>((a0 + a1) + (a2 + a3), scratch);
+    if (threadIdx.x == 0) {
         if (ssq_out) ssq_out[c] = acc;
         if (loss_out) loss_out[c] = div_rn(acc, two_sigma2);
     }
@@ -427,6 +438,9 @@ __global__ void div_check_kernel(const double* __restrict__ x, int64_t n, double
     const double a = div_const(x[k], dd, r), b = div_rn(x[k], dd);
     if (__double_as_longlong(a) != __double_as_longlong(b) && !(a != a && b != b)) atomicAdd(mismatches, 1ull);
 }
+
+#include "stencil_tma.cuh"
+static_assert(R2_TH == RS_TH && R2_WARPS == RS_WARPS && R2_TW == RS_TW, "both stencil kernels share the partial-sum tiling");
 
 static int tiles_x(const gmc_ctx* c) { return (c->W + RS_TW - 1) / RS_TW; }
 static int tiles_y(const gmc_ctx* c) { return (c->H + RS_TH - 1) / RS_TH; }
@@ -450,6 +464,40 @@ static int check_common(gmc_ctx* c, const void* p, int C, const char* who) {
     if (C < 1 || C > c->max_chains) GMC_FAIL(GMC_ESHAPE, "%s: C=%d outside [1,%d]", who, C, c->max_chains);
     GMC_CUDA(cudaSetDevice(c->device));
     return GMC_OK;
+}
+
+// TMA path (even W, 16-byte aligned bases): tensor maps over this call's bed / residual arrays, chain groups sized for the
+// kernel's own occupancy.  Returns false when it does not apply (the caller then launches residual_kernel).
+template <bool WR, bool LS, bool TST>
+static bool launch_tma_variant(gmc_ctx* c, cudaStream_t st, const double* bed, double* res, int C, double* partials) {
+    CUtensorMap tm_bed, tm_out;
+    if (!r2_encode(&tm_bed, bed, C, c->H, c->W, R2_BOXW, R2_BOXH)) return false;
+    if (!r2_encode(&tm_out, WR ? res : bed, C, c->H, c->W, R2_TW, R2_RW)) return false;
+    const int smem = r2_layout(WR && TST, LS).total;
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        if (cudaFuncSetAttribute(residual_tma_kernel<WR, LS, TST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, residual_tma_kernel<WR, LS, TST>, R2_THREADS, smem);
+        ctas_per_sm = nb > 0 ? nb : 1;
+    }
+    const int tx = (c->W + R2_TW - 1) / R2_TW, ty = (c->H + R2_TH - 1) / R2_TH;
+    const int slots = ctas_per_sm * c->sm_count;
+    int groups = 1;
+    double best = -1.0;
+    for (int G = 1; G <= std::max(1, std::min(C / 4, 1024)); ++G) {
+        const double n = (double)C / G, waves = (double)tx * ty * G / slots;
+        const double score = n / (n + 3.0) * (waves / std::ceil(waves)) * (waves < 1.0 ? waves : 1.0);
+        if (score > best + 1e-9) {
+            best = score;
+            groups = G;
+        }
+    }
+    if (const char* e = getenv("GMC_RS_GROUPS")) groups = std::max(1, std::min(atoi(e), C));
+    groups = std::min(groups, 65535);
+    residual_tma_kernel<WR, LS, TST><<<dim3(tx, ty, groups), R2_THREADS, smem, st>>>(tm_bed, tm_out, c->dev, res, partials, c->n_tiles, C,
+                                                                                c->dev.r_res, c->dev.r_two_res);
+    return true;
 }
 
 template <bool WR, bool LS>
@@ -492,12 +540,33 @@ static int launch_residual(gmc_ctx* c, const double* bed, double* res_out, doubl
     const dim3 grid(tx, ty, groups);
     // 16-byte accesses need even W and 16 B aligned bases
     const bool vec = (c->W % 2 == 0) && ((uintptr_t)bed % 16 == 0) && (!res_out || (uintptr_t)res_out % 16 == 0);
+    static const bool legacy = getenv("GMC_RS_LEGACY") != nullptr;      // A/B switch: the cp.async kernel of round 1
+    if (vec && !legacy) {
+        // residual tile out through TMA tensor stores (GMC_RS_TMA_STORE=1) or 16-byte streaming stores (default: measured
+        // 81.7 % vs 75.1 % of the HBM peak at 256 x 500^2, 90.6 % vs 91.3 % at 128 x 2000^2 - profiles/README.md)
+        static const bool tma_store = getenv("GMC_RS_TMA_STORE") && getenv("GMC_RS_TMA_STORE")[0] == '1';
+        bool ok;
+        if (res_out && do_loss) ok = tma_store ? launch_tma_variant<true, true, true>(c, st, bed, res_out, C, partials)
+                                               : launch_tma_variant<true, true, false>(c, st, bed, res_out, C, partials);
+        else if (res_out) ok = tma_store ? launch_tma_variant<true, false, true>(c, st, bed, res_out, C, partials)
+                                         : launch_tma_variant<true, false, false>(c, st, bed, res_out, C, partials);
+        else ok = launch_tma_variant<false, true, false>(c, st, bed, res_out, C, partials);
+        if (ok) {
+            c->launches++;
+            if (do_loss) {
+                finalize_loss_kernel<<<C, FIN_THREADS, 0, st>>>(partials, c->n_tiles, c->dev.two_sigma2, loss_out, ssq_out, C);
+                c->launches++;
+            }
+            GMC_CUDA(cudaGetLastError());
+            return GMC_OK;
+        }
+    }
     if (res_out && do_loss) launch_variant<true, true>(c, grid, st, bed, res_out, C, vec, partials);
     else if (res_out) launch_variant<true, false>(c, grid, st, bed, res_out, C, vec, partials);
     else launch_variant<false, true>(c, grid, st, bed, res_out, C, vec, partials);
     c->launches++;
     if (do_loss) {
-        finalize_loss_kernel<<<(C + 7) / 8, 256, 0, st>>>(partials, c->n_tiles, c->dev.two_sigma2, loss_out, ssq_out, C);
+        finalize_loss_kernel<<<C, FIN_THREADS, 0, st>>>(partials, c->n_tiles, c->dev.two_sigma2, loss_out, ssq_out, C);
         c->launches++;
     }
     GMC_CUDA(cudaGetLastError());
@@ -545,7 +614,7 @@ extern "C" int gmc_loss(gmc_ctx* c, const double* res, double* loss_out, double*
                                                               c->d_partials + (size_t)c0 * chunks, chunks);
         c->launches++;
     }
-    finalize_loss_kernel<<<(C + 7) / 8, 256, 0, st>>>(c->d_partials, chunks, c->dev.two_sigma2, loss_out, ssq_out, C);
+    finalize_loss_kernel<<<C, FIN_THREADS, 0, st>>>(c->d_partials, chunks, c->dev.two_sigma2, loss_out, ssq_out, C);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;

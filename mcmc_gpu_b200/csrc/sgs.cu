@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(SGS_THREADS)
     sgs_run_kernel(GmcDev d, SgsDev s, double* bedc_all, double* z_all, double* mcres_all, double* ssq_all, int32_t* nviol_all,
                    const uint64_t* __restrict__ seeds, uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache,
                    int32_t* blocks_cache, int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int32_t* err_out,
-                   int C, int* sched, int chunk) {
+                   int C, int* sched, int chunk, int* dev_err, unsigned spin_limit) {
     extern __shared__ __align__(16) unsigned char sgs_raw[];
     SgsShared& S = *reinterpret_cast<SgsShared*>(sgs_raw);
     __shared__ long long s_item;
@@ -862,7 +862,11 @@ __global__ void __launch_bounds__(SGS_THREADS)
                     unsigned spins = 0;
                     while (*done < jj) {
                         __nanosleep(200);
-                        if (++spins > (1u << 26)) break;      // cannot happen: an item only waits for items drawn earlier
+                        if (++spins > spin_limit) {           // an item only waits for items drawn earlier; never hang, and
+                            *(volatile int*)dev_err = GMC_DEVERR_WAIT_TIMEOUT;   // never carry on silently (host: GMC_ECUDA)
+                            __threadfence_system();
+                            break;
+                        }
                     }
                     __threadfence();
                 }
@@ -1087,6 +1091,10 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
         GMC_FAIL(GMC_ESHAPE, "gmc_sgs_run: cache window exceeds stride");
     if (n_steps == 0) return GMC_OK;
     c->sgs->dev.phase = c->d_phase;
+    {
+        int rc1 = gmc_check_device_error(c, "gmc_sgs_run");
+        if (rc1) return rc1;
+    }
     // more chains than resident CTAs: dynamic (chunk, chain) items, see sgs_run_kernel
     int per_sm = 0;
     if (c->sgs->warp_solver)
@@ -1099,21 +1107,20 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
     if (C > slots && n_steps > 1 && !getenv("GMC_STATIC_SCHED")) {
         // launches for disjoint chain ranges may run concurrently on different streams (run_pipelined): each takes the
         // next of GMC_SCHED_SLOTS scheduler areas
-        const size_t area = (size_t)c->max_chains + 1;
-        if (!c->d_sched) GMC_CUDA(cudaMalloc(&c->d_sched, GMC_SCHED_SLOTS * area * sizeof(int)));
-        sched = c->d_sched + (size_t)(c->sched_next++ % GMC_SCHED_SLOTS) * area;
-        GMC_CUDA(cudaMemsetAsync(sched, 0, (size_t)(C + 1) * sizeof(int), (cudaStream_t)stream));
+        int rc2 = gmc_sched_acquire(c, C, (cudaStream_t)stream, &sched);
+        if (rc2) return rc2;
         grid = slots;
         chunk = std::min(256, std::max(2, (n_steps + 31) / 32));   // see gmc_run (step.cu)
     }
     if (c->sgs->warp_solver)
         sgs_run_kernel<true><<<grid, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
             c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
-            cache_offset, resampled, err_flag, C, sched, chunk);
+            cache_offset, resampled, err_flag, C, sched, chunk, c->d_err, c->spin_limit);
     else
         sgs_run_kernel<false><<<grid, SGS_THREADS, sizeof(SgsShared), (cudaStream_t)stream>>>(
             c->dev, c->sgs->dev, bedc, z, mcres, ssq, nviol, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride,
-            cache_offset, resampled, err_flag, C, sched, chunk);
+            cache_offset, resampled, err_flag, C, sched, chunk, c->d_err, c->spin_limit);
+    if (sched) gmc_sched_release(c, (cudaStream_t)stream);
     c->launches++;
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;

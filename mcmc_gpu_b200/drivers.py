@@ -226,12 +226,21 @@ def smallScaleChain_mp(n_chains, n_workers, smallScaleChain, initial_beds, ssc_r
 # ensemble statistics: the one collective on the path
 # ---------------------------------------------------------------------------------------------------------------------
 def allreduce_moments(sum_, sumsq, count, group=None):
-    """In-place SUM all-reduce of (sum, sumsq, count) over the ranks; tensors may be CUDA (NCCL) or CPU (gloo)."""
+    """In-place SUM all-reduce of (sum, sumsq, count) over the ranks as ONE packed buffer of 2*H*W+1 doubles (one collective
+    launch instead of three); tensors may be CUDA (NCCL) or CPU (gloo)."""
     rank, world = dist_info()
     if world > 1:
+        import torch
         import torch.distributed as dist
-        for t in (sum_, sumsq, count):
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        n = sum_.numel()
+        packed = torch.empty(2 * n + 1, dtype=sum_.dtype, device=sum_.device)
+        packed[:n] = sum_.reshape(-1)
+        packed[n:2 * n] = sumsq.reshape(-1)
+        packed[2 * n] = count.reshape(-1)[0]
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        sum_.copy_(packed[:n].reshape(sum_.shape))
+        sumsq.copy_(packed[n:2 * n].reshape(sumsq.shape))
+        count.copy_(packed[2 * n:2 * n + 1].reshape(count.shape))
     return sum_, sumsq, count
 
 

@@ -28,8 +28,50 @@ def test_pairs_tapers_and_weights_equal_the_oracle(name):
     ref = O.edge_taper_masks(pairs, case["logistic"], case["max_dist"], g["resolution"])   # KD-tree, like the reference
     for a, b in zip(rf.edge_masks, ref):
         assert bits_equal(a, b)
-    w = rf.get_crf_weight(g["xx"], g["yy"], g["data_mask"])[0]
+    # the logistic on a given distance map is host logic; the distance map itself is a GPU kernel (tests/test_gpu_residual.py)
+    from scipy.spatial import cKDTree
+    sel = g["data_mask"] == 1
+    dist = cKDTree(np.column_stack([g["xx"][sel], g["yy"][sel]])).query(
+        np.column_stack([g["xx"].ravel(), g["yy"].ravel()]))[0].reshape(g["xx"].shape)
+    w = rf.get_crf_weight_from_dist(g["xx"], g["yy"], dist)[0]
     assert bits_equal(w, O.crf_data_weight(g["xx"], g["yy"], g["data_mask"], tuple(case["logistic"]), case["max_dist"]))
+
+
+def test_crf_weight_has_no_cpu_fallback():
+    """north_star: no CPU fallback - without a CUDA device the weight setup raises instead of quietly using scipy."""
+    import torch
+    from mcmc_gpu_b200._lib import GmcError
+    if torch.cuda.is_available():
+        pytest.skip("needs a host without a CUDA device")
+    case = TRAJECTORY_CASES[sorted(TRAJECTORY_CASES)[0]]
+    g = build_case_grids(case)
+    rf = _rf(case)
+    rf.set_weight_param(*case["logistic"], case["max_dist"], g["resolution"])
+    with pytest.raises(GmcError):
+        rf.get_crf_weight(g["xx"], g["yy"], g["data_mask"])
+
+
+def test_context_cache_key_follows_the_randfield_contents():
+    """a setter call on RF (or a re-created RF) must change the key the chain caches its device context under."""
+    case = TRAJECTORY_CASES[sorted(TRAJECTORY_CASES)[0]]
+    g = build_case_grids(case)
+    rf = _rf(case)
+    rf.set_weight_param(*case["logistic"], case["max_dist"], g["resolution"])
+    k0 = rf._config_key()
+    assert _rf_same(case, g)._config_key() == k0                   # same contents, different object: same key
+    rf.set_block_sizes(case["blocks"][0] + 2, *case["blocks"][1:])
+    rf.set_weight_param(*case["logistic"], case["max_dist"], g["resolution"])
+    assert rf._config_key() != k0
+    rf2 = _rf_same(case, g)
+    L = list(case["logistic"])
+    rf2.set_weight_param(L[0], L[1], L[2] + 1.0, L[3], case["max_dist"], g["resolution"])
+    assert rf2._config_key() != k0
+
+
+def _rf_same(case, g):
+    rf = _rf(case)
+    rf.set_weight_param(*case["logistic"], case["max_dist"], g["resolution"])
+    return rf
 
 
 def test_taper_with_awkward_resolution():
