@@ -186,15 +186,23 @@ __device__ __forceinline__ void r2_rows(const R2Lane& L, const GmcDev& d, unsign
             }
         }
     }
-    acc = 0.0;
+    double v[R2_RW][2];
 #pragma unroll
     for (int k = 0; k < R2_RW; ++k) {
         r[k].x = sub_rn(add_rn(add_rn(quo[k][0], quo[k][2]), L.dh[k].x), L.sm[k].x);
         r[k].y = sub_rn(add_rn(add_rn(quo[k][1], quo[k][3]), L.dh[k].y), L.sm[k].y);
-        if (DO_LOSS) {                                             // bits of rows / columns outside the grid are 0
-            if (((mcbits >> (2 * k)) & 1u) && r[k].x == r[k].x) acc = add_rn(acc, mul_rn(r[k].x, r[k].x));
-            if (((mcbits >> (2 * k + 1)) & 1u) && r[k].y == r[k].y) acc = add_rn(acc, mul_rn(r[k].y, r[k].y));
+        if (DO_LOSS) {
+            // four independent masked squares, then a tree: a sequential `if (...) acc += r*r` chain compiled to a serial
+            // select-and-move sequence twice as long (bits of rows / columns outside the grid are 0; nan cells count 0)
+            const double s0 = mul_rn(r[k].x, r[k].x), s1 = mul_rn(r[k].y, r[k].y);
+            v[k][0] = (((mcbits >> (2 * k)) & 1u) && s0 == s0) ? s0 : 0.0;
+            v[k][1] = (((mcbits >> (2 * k + 1)) & 1u) && s1 == s1) ? s1 : 0.0;
         }
+    }
+    acc = 0.0;
+    if (DO_LOSS) {
+        static_assert(R2_RW == 2, "the loss tree is written for two rows per warp");
+        acc = add_rn(add_rn(v[0][0], v[0][1]), add_rn(v[1][0], v[1][1]));
     }
 }
 

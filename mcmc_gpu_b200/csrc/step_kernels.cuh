@@ -759,7 +759,8 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
             const int64_t idx = (int64_t)(s.x0 + bi) * W + (s.y0 + bj);
             __stcg(bed + idx, tile[(bi + 1) * tp + (bj + 1)]);
             __stcg(mcres + idx, newres[e]);
-            if (resampled && (__ldg(d.flags + idx) & FLAG_GATE)) __stcg(resampled + idx, __ldcg(resampled + idx) + 1);
+            // coverage count (MCMC.py:1349-1352): a fire-and-forget L2 reduction instead of a load + store round trip
+            if (resampled && (__ldg(d.flags + idx) & FLAG_GATE)) atomicAdd(resampled + idx, 1);
         }
     }
     __syncthreads();   // write-back visible to the next iteration's tile load; smem free for reuse
