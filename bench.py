@@ -358,7 +358,7 @@ def target_run(torch, dist, MCMC, syn, quiet, world, rank, local, dev, H, W, C, 
     out = {"workload": label, "grid": [H, W], "chains_per_gpu": C, "chains_total": total_c, "n_gpus": world, "iters_per_step": n_it,
            "steps": steps, "warmup": warmup, "value": value, "unit": UNIT, "ms_per_step": total_ms / steps,
            "per_gpu_value": value / world, "acceptance_rate": float(st.mean()),
-           "state_gb_per_gpu": 2 * C * H * W * 8 / 1e9, "step_kernel": batch.ctx.step_kernel_info(),
+           "state_gb_per_gpu": 2 * C * H * W * 8 / 1e9, "step_kernel": batch.ctx.step_kernel_info(C),
            "roofline_U3": {"achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                            "algorithmic_bytes_per_chain_step": by / (C * n_it)},
            "stencil": {"U1_frac": cells * 16 / (ms_u1 * 1e-3) / 1e9 / peak, "U1_ms": ms_u1,
@@ -478,7 +478,7 @@ def gpu_main(a):
     g, ch, rf = build_chain(MCMC, syn, H, W, quiet)
     seeds = [1000 + chain0 + c for c in range(C)]                   # global chain id -> seed: invariant to GPU count
     n_it = a.iters
-    NBUF = 2                                                        # e2e: two steps in flight (double-buffered device state)
+    NBUF = int(os.environ.get("GMC_E2E_STEPS_IN_FLIGHT", "3"))      # e2e: steps in flight (multi-buffered device state)
 
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype).pin_memory()
@@ -491,7 +491,7 @@ def gpu_main(a):
     batches = [MCMC.ChainBatch(ch, rf, host_beds, keys, device=dev, track_resampled=True) for _ in range(NBUF)]
     batch = batches[0]
     ctx = batch.ctx
-    info = ctx.step_kernel_info()
+    info = ctx.step_kernel_info(C)
     peak, peak_src = measured_peak()
 
     # ---- (1) device-resident throughput: inputs already in HBM ---------------------------------------------------

@@ -8,6 +8,8 @@ struct SpecParams {
     double nu;
     double constant; // Matern prefactor
     double kappa;    // 2 nu / a^2
+    double amp0;     // sqrt(S) = amp0 * exp(qexp * L): L = (a k)^2 (Gaussian), log(1 + (a k)^2) (Exponential),
+    double qexp;     //                                  log(kappa + 4 pi k^2) (Matern)
 };
 
 struct StepScalars {
@@ -40,6 +42,42 @@ struct PhaseClock {
         }
     }
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Canonical reductions: the step kernels exist for two CTA sizes, and a chain's trajectory must not depend on which one
+// advances it (bit-identical across batch compositions and GPU counts).  Every sum over a CTA is therefore defined over V
+// virtual slots - item q belongs to slot q mod V, slots accumulate in increasing q, groups of 32 slots are summed by the
+// warp shuffle tree, the V/32 group sums by one more shuffle tree - and a CTA with fewer than V working threads keeps
+// V / workers accumulators per thread (thread t: slots t, t + workers, ...).
+// ---------------------------------------------------------------------------------------------------------------
+#define GMC_SUM_SLOTS 512                                  // fill power, residual re-sum: all threads work
+#define GMC_SUM_NACC (GMC_SUM_SLOTS / GMC_STEP_THREADS)    // 2 (256 threads) or 1 (512 threads)
+#define GMC_TAIL_SLOTS 448                                 // residual phase: 14 worker warps' worth
+#define GMC_TAIL_WORKERS (GMC_STEP_THREADS == 256 ? 224 : 448)
+#define GMC_TAIL_NACC (GMC_TAIL_SLOTS / GMC_TAIL_WORKERS)
+static_assert(GMC_SUM_NACC * GMC_STEP_THREADS == GMC_SUM_SLOTS && GMC_TAIL_NACC * GMC_TAIL_WORKERS == GMC_TAIL_SLOTS, "CTA size");
+
+// acc[a] = partial sum of slot a * WORKERS + threadIdx.x (threads >= WORKERS pass zeros).  Result valid in all threads.
+template <int NACC, int WORKERS>
+__device__ __forceinline__ double canon_block_sum(const double (&acc)[NACC], double* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int GROUPS = NACC * WORKERS / 32;
+    static_assert(GROUPS <= 32, "one final warp");
+    __syncthreads();                       // protect scratch from a previous use
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+        const double v = warp_sum(acc[a]);
+        if (lane == 0 && wid < WORKERS / 32) scratch[a * (WORKERS / 32) + wid] = v;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        double t = (lane < GROUPS) ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // complex helpers
@@ -213,6 +251,111 @@ __device__ __noinline__ void fft_lines(double2* Z, int line_stride, int elem_str
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Lean FP64 elementary functions for the spectrum fill.  The fill is 38 percent of the step kernel's instructions and it is
+// issue bound; libdevice's log / exp / sincospi / sqrt spend half of theirs on argument classes that cannot occur here
+// (zero, negative, subnormal, inf, nan, huge).  These versions assume positive, normal, moderately sized arguments and keep
+// full double accuracy (<= 3.2e-16 relative against 120-bit references on millions of points, the prototype is kept in
+// profiles/lean_math_check.py): fdlibm's log kernel, a degree-13 Taylor exp on |r| <= ln2/2, Taylor sin/cos of pi r on
+// |r| <= 1/4 after an exact reduction, and Newton square roots / reciprocals seeded by the single-precision units.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double lean_rcp(double d) {                 // 1/d, d in [1.7, 3.5]
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"((float)d));
+    double r = (double)rf;
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
+__device__ __forceinline__ double lean_sqrt(double x) {                // x > 0, normal, within float range
+    float yf;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yf) : "f"((float)x));
+    double y = (double)yf;
+    const double h = 0.5 * x;
+    y = y * fma(-(h * y), y, 1.5);
+    y = y * fma(-(h * y), y, 1.5);
+    const double g = x * y;
+    return fma(fma(-g, g, x), 0.5 * y, g);
+}
+__device__ __forceinline__ double lean_log(double x) {                 // x > 0, normal
+    int hi = __double2hiint(x);
+    const int lo = __double2loint(x);
+    int e = (hi >> 20) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    if (hi >= 0x3ff6a09f) {                                            // mantissa above sqrt(2): halve it
+        hi -= 0x00100000;
+        e += 1;
+    }
+    const double f = __hiloint2double(hi, lo) - 1.0;                   // in [-0.2929, 0.4143)
+    const double s = f * lean_rcp(2.0 + f);
+    const double z = s * s;
+    double R = fma(z, 1.479819860511658591e-01, 1.531383769920937332e-01);
+    R = fma(z, R, 1.818357216161805012e-01);
+    R = fma(z, R, 2.222219843214978396e-01);
+    R = fma(z, R, 2.857142874366239149e-01);
+    R = fma(z, R, 3.999999999940941908e-01);
+    R = fma(z, R, 6.666666666666735130e-01);
+    R *= z;
+    const double lm = fma(s, R, s + s);                                // log(1 + f) = 2 s + s R
+    const double de = (double)e;
+    return fma(de, 6.93147180369123816490e-01, fma(de, 1.90821492927058770002e-10, lm));
+}
+__device__ __forceinline__ double lean_exp(double y) {                 // |y| < 700
+    const double magic = 6755399441055744.0;                           // 1.5 * 2^52: rounds to the nearest integer
+    const double t = fma(y, 1.4426950408889634074, magic);
+    const int k = __double2loint(t);
+    const double kd = t - magic;
+    double r = fma(-kd, 6.93147180369123816490e-01, y);
+    r = fma(-kd, 1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;
+    p = fma(p, r, 2.08767569878681e-09);
+    p = fma(p, r, 2.505210838544172e-08);
+    p = fma(p, r, 2.755731922398589e-07);
+    p = fma(p, r, 2.7557319223985893e-06);
+    p = fma(p, r, 2.48015873015873e-05);
+    p = fma(p, r, 0.0001984126984126984);
+    p = fma(p, r, 0.001388888888888889);
+    p = fma(p, r, 0.008333333333333333);
+    p = fma(p, r, 0.041666666666666664);
+    p = fma(p, r, 0.16666666666666666);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+// sin and cos of 2 pi u, u in (0, 1)
+__device__ __forceinline__ void lean_sincos2pi(double u, double& sn, double& cs) {
+    const double magic = 6755399441055744.0;
+    const double t4 = 4.0 * u;                                         // quarter turns
+    const double tm = t4 + magic;
+    const int j = __double2loint(tm);                                  // nearest quarter turn, 0..4
+    const double r = 0.5 * (t4 - (tm - magic));                        // exact; sin(pi r), cos(pi r) with |r| <= 1/4
+    const double z = r * r;
+    double sp = 7.952054001475508e-07;
+    sp = fma(sp, z, -2.1915353447830204e-05);
+    sp = fma(sp, z, 0.00046630280576761234);
+    sp = fma(sp, z, -0.007370430945714348);
+    sp = fma(sp, z, 0.08214588661112819);
+    sp = fma(sp, z, -0.5992645293207919);
+    sp = fma(sp, z, 2.550164039877345);
+    sp = fma(sp, z, -5.167712780049969);
+    sp = fma(sp, z, 3.141592653589793);
+    sp *= r;
+    double cp = -1.387895246221376e-07;
+    cp = fma(cp, z, 4.303069587032944e-06);
+    cp = fma(cp, z, -0.00010463810492484565);
+    cp = fma(cp, z, 0.001929574309403922);
+    cp = fma(cp, z, -0.02580689139001405);
+    cp = fma(cp, z, 0.23533063035889312);
+    cp = fma(cp, z, -1.3352627688545893);
+    cp = fma(cp, z, 4.058712126416768);
+    cp = fma(cp, z, -4.934802200544679);
+    cp = fma(cp, z, 1.0);
+    const double a = (j & 1) ? cp : sp, b = (j & 1) ? sp : cp;
+    sn = __hiloint2double(__double2hiint(a) ^ ((j & 2) << 30), __double2loint(a));
+    cs = __hiloint2double(__double2hiint(b) ^ (((j + 1) & 2) << 30), __double2loint(b));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // spectral amplitude sqrt(S(k))                                                          MCMC.py:209-239
 // ---------------------------------------------------------------------------------------------------------------
 // x^p for x > 0 as exp(p log x): relative error ~ |p log x| 2^-53 (<= 1e-14 here), about half the cost of pow()
@@ -241,54 +384,46 @@ __device__ __forceinline__ SpecParams make_spec(const GmcFieldModel& fm, double 
         sp.constant = div_rn(fm.matern_num, mul_rn(fm.matern_gamma, pow_pos(sp.a, mul_rn(2.0, sp.nu))));
         sp.kappa = div_rn(mul_rn(2.0, sp.nu), mul_rn(sp.a, sp.a));
     }
+    sp.amp0 = (fm.model == GMC_MATERN) ? sqrt(sp.constant) : 1.0;
+    sp.qexp = (fm.model == GMC_GAUSSIAN) ? -0.25 : (fm.model == GMC_EXPONENTIAL ? -0.75 : -0.5 * (sp.nu + 1.0));
     return sp;
 }
 
-__device__ __noinline__ double spec_amp(const SpecParams& sp, double ksq_sum) {
-    const double k = add_rn(sqrt(ksq_sum), 1e-10);
-    double S;
+// sqrt(S(k)) for k^2 = ksq_sum (MCMC.py:224-239: k = sqrt(kx^2 + ky^2) + 1e-10, S by model, then sqrt): the square root of
+// the density is folded into the exponent, amp0 * exp(qexp * L) - equal to the reference's sqrt(S) to ~1e-15 relative
+// (the parity bar for fields is 1e-9 of max|f|).
+__device__ __forceinline__ double spec_sqrt_density(const SpecParams& sp, double ksq_sum) {
+    const double k = add_rn((ksq_sum > 0.0) ? lean_sqrt(ksq_sum) : 0.0, 1e-10);
+    double L;
     if (sp.model == GMC_GAUSSIAN) {
         const double ak = mul_rn(sp.a, k);
-        S = exp(mul_rn(-0.5, mul_rn(ak, ak)));
+        L = mul_rn(ak, ak);
     } else if (sp.model == GMC_EXPONENTIAL) {
         const double ak = mul_rn(sp.a, k);
-        S = div_rn(1.0, pow_pos(add_rn(1.0, mul_rn(ak, ak)), 1.5));
+        L = lean_log(add_rn(1.0, mul_rn(ak, ak)));
     } else {
         const double four_pi = 4 * 3.141592653589793;
-        S = mul_rn(sp.constant, pow_pos(add_rn(sp.kappa, mul_rn(four_pi, mul_rn(k, k))), sub_rn(-sp.nu, 1.0)));
+        L = lean_log(add_rn(sp.kappa, mul_rn(four_pi, mul_rn(k, k))));
     }
-    return sqrt(S);
+    return sp.amp0 * lean_exp(sp.qexp * L);
 }
+__device__ __noinline__ double spec_amp(const SpecParams& sp, double ksq_sum) { return spec_sqrt_density(sp, ksq_sum); }
 
 // One spectrum item of the device-RNG path: sqrt(S) and the two complex normals of its mirrored rows.  A single
-// out-of-line body (one copy in the instruction cache) in which the three dependency chains — log/exp of the density,
-// log/sqrt/sincospi of the two Box-Muller draws — are independent, so the scheduler interleaves them.
+// out-of-line body (one copy in the instruction cache) in which the three dependency chains - log/exp of the density,
+// log/sqrt/sincos of the two Box-Muller draws - are independent, so the scheduler interleaves them.
 struct FillItem {
     double amp, z0, z1, y0, y1;
 };
-__device__ __forceinline__ double spec_density(const SpecParams& sp, double ksq_sum) {
-    const double k = add_rn(sqrt(ksq_sum), 1e-10);
-    if (sp.model == GMC_GAUSSIAN) {
-        const double ak = mul_rn(sp.a, k);
-        return exp(mul_rn(-0.5, mul_rn(ak, ak)));
-    }
-    if (sp.model == GMC_EXPONENTIAL) {
-        const double ak = mul_rn(sp.a, k);
-        return div_rn(1.0, pow_pos(add_rn(1.0, mul_rn(ak, ak)), 1.5));
-    }
-    const double four_pi = 4 * 3.141592653589793;
-    return mul_rn(sp.constant, pow_pos(add_rn(sp.kappa, mul_rn(four_pi, mul_rn(k, k))), sub_rn(-sp.nu, 1.0)));
-}
 __device__ __noinline__ void fill_item(const SpecParams& sp, const Philox& rng, uint32_t it_lo, uint32_t it_hi, double ks,
                                        uint32_t e0, uint32_t e1, FillItem& r) {
     const uint4 a = rng(e0, it_lo, it_hi, GMC_STREAM_NOISE), b = rng(e1, it_lo, it_hi, GMC_STREAM_NOISE);
-    const double l0 = log(u01_open(a.x, a.y)), l1 = log(u01_open(b.x, b.y));
+    const double l0 = lean_log(u01_open(a.x, a.y)), l1 = lean_log(u01_open(b.x, b.y));
     double s0, c0, s1, c1;
-    sincospi(2.0 * u01_open(a.z, a.w), &s0, &c0);
-    sincospi(2.0 * u01_open(b.z, b.w), &s1, &c1);
-    const double S = spec_density(sp, ks);
-    const double q0 = sqrt(-2.0 * l0), q1 = sqrt(-2.0 * l1);
-    r.amp = sqrt(S);
+    lean_sincos2pi(u01_open(a.z, a.w), s0, c0);
+    lean_sincos2pi(u01_open(b.z, b.w), s1, c1);
+    r.amp = spec_sqrt_density(sp, ks);
+    const double q0 = lean_sqrt(-2.0 * l0), q1 = lean_sqrt(-2.0 * l1);
     r.z0 = q0 * c0;
     r.z1 = q0 * s0;
     r.y0 = q1 * c1;
@@ -375,7 +510,10 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
     // (1) fill the Hermitian half plane (ky in [0,h), kx in [0,w/2]) at the digit-reversed row position of the column
     // pass; one item per (|ky| = a, kx): the entries ky = a and ky = h-a share sqrt(S).  Accumulate the power for the
     // variance (Parseval): interior columns count twice (their mirror images kx > w/2 are not stored).
-    double power = 0.0;
+    double power[GMC_SUM_NACC];                                    // canonical slots, see canon_block_sum
+#pragma unroll
+    for (int a = 0; a < GMC_SUM_NACC; ++a) power[a] = 0.0;
+    int trip = 0;                                                  // this thread's trip count: selects the accumulator
     const FastDiv dhc(hc);
     const int n_items = (h / 2 + 1) * hc;
     // store one item's (up to) two entries and accumulate their power
@@ -384,12 +522,15 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
         const bool edge_x = (kx == 0 || kx == n2);
         if (a == 0 && kx == 0) X0 = X1 = make_double2(0.0, 0.0);   // DC: removed by the mean subtraction (MCMC.py:248)
         const double wgt = edge_x ? 1.0 : 2.0;
-        power += wgt * (X0.x * X0.x + X0.y * X0.y);
+        double pw = wgt * (X0.x * X0.x + X0.y * X0.y);
         Z[posY[a] * pitchc + kx] = X0;
         if (!self_y) {
-            power += wgt * (X1.x * X1.x + X1.y * X1.y);
+            pw += wgt * (X1.x * X1.x + X1.y * X1.y);
             Z[posY[h - a] * pitchc + kx] = X1;
         }
+        if (GMC_SUM_NACC == 1 || (trip & 1) == 0) power[0] += pw;
+        else power[GMC_SUM_NACC - 1] += pw;
+        ++trip;
     };
     if (INJECT) {
         for (int q = threadIdx.x; q < n_items; q += GMC_STEP_THREADS) {
@@ -419,10 +560,10 @@ __device__ FieldView synth_field(const GmcDev& d, double* buf, double* scratch, 
             emit(a, kx, X0, X1);
         }
     }
-    power = block_sum<GMC_STEP_THREADS>(power, scratch);           // also orders the fill before the column pass
+    const double power_sum = canon_block_sum<GMC_SUM_NACC, GMC_STEP_THREADS>(power, scratch);   // also orders the fill before the column pass
     // field = (1/(hw)) sum_k X_h e^{...};  var = power/(hw)^2;  (x - mean)/(std + 1e-12) * scale   MCMC.py:247-250
     const double inv_n = 1.0 / ((double)h * (double)w);
-    const double sd = sqrt(power) * inv_n;
+    const double sd = sqrt(power_sum) * inv_n;
     const double cscale = scale / (sd + 1e-12) * inv_n;
     pc.mark(1);
 
@@ -693,11 +834,16 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
     pc.mark(5);
 
     // phase B: residual on the block, loss delta, thickness guard                       MCMC.py:1292-1329
-    double delta = 0.0;
+    double delta[GMC_TAIL_NACC];                                   // canonical slots, see canon_block_sum
+#pragma unroll
+    for (int a = 0; a < GMC_TAIL_NACC; ++a) delta[a] = 0.0;
+    int trip = 0;
     int bad = 0;
-    constexpr int B_THREADS = HELPER ? GMC_STEP_THREADS - 32 : GMC_STEP_THREADS;
-    if (HELPER && threadIdx.x >= B_THREADS) prepare_step(d, rng, next->it, *next->sc, *next->pair, *next->tab, next->vec);
-    for (int e = (HELPER && threadIdx.x >= B_THREADS) ? bh * bw : threadIdx.x; e < bh * bw; e += B_THREADS) {
+    // workers: 224 threads (7 warps) of a 256-thread CTA, 448 (14 warps) of a 512-thread one; with HELPER the last warp
+    // prepares the next step instead (and warp 14 of the wide CTA idles here)
+    constexpr int B_THREADS = GMC_TAIL_WORKERS;
+    if (HELPER && threadIdx.x >= GMC_STEP_THREADS - 32) prepare_step(d, rng, next->it, *next->sc, *next->pair, *next->tab, next->vec);
+    for (int e = (threadIdx.x >= B_THREADS) ? bh * bw : threadIdx.x; e < bh * bw; e += B_THREADS, ++trip) {
         const int bi = dbw.div(e), bj = e - bi * bw;
         const int i = s.x0 + bi, j = s.y0 + bj;
         const double* tc = tile + (bi + 1) * tp + (bj + 1);
@@ -724,12 +870,13 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
         const double rnew = sub_rn(add_rn(add_rn(dx, dy), hs.x), hs.y);
         newres[e] = rnew;
         if (fl & FLAG_MC) {
-            if (rnew == rnew && rold == rold) delta += (rnew - rold) * (rnew + rold);
-            else delta += sq_or_zero(rnew) - sq_or_zero(rold);
+            const double dl = (rnew == rnew && rold == rold) ? (rnew - rold) * (rnew + rold) : sq_or_zero(rnew) - sq_or_zero(rold);
+            if (GMC_TAIL_NACC == 1 || (trip & 1) == 0) delta[0] += dl;
+            else delta[GMC_TAIL_NACC - 1] += dl;
         }
         if ((fl & FLAG_GATE) && sub_rn(sc0, tc[0]) <= 0.0) bad = 1;
     }
-    const double dsum = block_sum<GMC_STEP_THREADS>(delta, scratch);
+    const double dsum = canon_block_sum<GMC_TAIL_NACC, GMC_TAIL_WORKERS>(delta, scratch);
     bad = __syncthreads_or(bad);
 
     // decision                                                                          MCMC.py:1331-1337
@@ -770,12 +917,17 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
 // full masked nansum of the tracked residual (fixed order)
 __device__ double resync_ssq(const GmcDev& d, const double* mcres, double* scratch) {
     const int64_t n = (int64_t)d.H * d.W;
-    double acc = 0.0;
-    for (int64_t k = threadIdx.x; k < n; k += GMC_STEP_THREADS) {
+    double acc[GMC_SUM_NACC];
+#pragma unroll
+    for (int a = 0; a < GMC_SUM_NACC; ++a) acc[a] = 0.0;
+    int trip = 0;
+    for (int64_t k = threadIdx.x; k < n; k += GMC_STEP_THREADS, ++trip) {
         const double v = __ldcg(mcres + k);
-        if ((__ldg(d.flags + k) & FLAG_MC) && v == v) acc += v * v;
+        const double sq = ((__ldg(d.flags + k) & FLAG_MC) && v == v) ? v * v : 0.0;
+        if (GMC_SUM_NACC == 1 || (trip & 1) == 0) acc[0] += sq;
+        else acc[GMC_SUM_NACC - 1] += sq;
     }
-    return block_sum<GMC_STEP_THREADS>(acc, scratch);
+    return canon_block_sum<GMC_SUM_NACC, GMC_STEP_THREADS>(acc, scratch);
 }
 
 // Everything a step needs before its field can be synthesised, computed by ONE warp: the step's scalars (block size, scale,
