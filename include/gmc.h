@@ -166,14 +166,16 @@ GMC_API int gmc_run(gmc_ctx* ctx, double* bed, double* mcres, double* ssq, const
  *   zcond [H][W]                  : normal-scored conditioning data, NaN where none (MCMC.py:1653-1661)
  *   grounded [H][W] u8            : grounded_ice_mask of the full-grid thickness guard (MCMC.py:1789-1795)
  *   quantiles, references [n_q]   : QuantileTransformer.quantiles_[:,0], references_ (NULL/NULL: do_transform=False)
- *   oct_off [8][lmax][2] i16, oct_cnt [8] : for octant b = -4..3 of neighbors.py:52-60 the window offsets (di, dj) with
- *                                   distance < radius, sorted by (distance, di, dj); hw = window half width in cells
+ *   oct_off [8][lmax][2] i16      : for octant b = -4..3 of neighbors.py:52-60 the window offsets (di, dj) with distance <
+ *                                   the WIDEST search radius, sorted by (distance, di, dj); hw = window half width in cells
+ *   oct_cnt [n_levels][8], n_levels: prefix lengths of those lists for radius, radius + 100 km, ...: a node that finds no
+ *                                   conditioned cell within `radius` searches again 100 km wider (MCMC.py:149-155)
  *   num_points                    : set_sgs_param neighbours (num_points//8 per octant)
  *   lut [(4hw+1)][(4hw+1)]        : covariance of the offset (di, dj), di,dj in [-2hw, 2hw] (covariance.py models)
  *   sill; block sizes             : variogram sill; set_block_sizes (sizes drawn from [min, max), MCMC.py:1755-1756) */
 GMC_API int gmc_sgs_setup(gmc_ctx* ctx, const double* trend, const double* zcond, const uint8_t* grounded,
                           const double* quantiles, const double* references, int n_quantiles, const int16_t* oct_off,
-                          const int32_t* oct_cnt, int lmax, int hw, int num_points, const double* lut, double sill,
+                          const int32_t* oct_cnt, int n_levels, int lmax, int hw, int num_points, const double* lut, double sill,
                           int block_min_x, int block_max_x, int block_min_y, int block_max_y);
 
 /* QuantileTransformer(output_distribution='normal').transform / inverse_transform of n values (dev), S5. */

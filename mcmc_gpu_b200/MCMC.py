@@ -621,9 +621,9 @@ class chain_sgs(chain):
             v["s"] = p[6]
         return v
 
-    def _sgs_context(self, max_chains, device=None):
+    def _sgs_context(self, max_chains, device=None, widen=False):
         from . import sgs_tables as T
-        key = ("sgs", max_chains, str(device))
+        key = ("sgs", max_chains, str(device), bool(widen))
         if self._ctx is not None and self._ctx_key == key:
             return self._ctx
         H, W = self.xx.shape
@@ -637,7 +637,16 @@ class chain_sgs(chain):
                        centre, None, self.resolution, self.sigma_mc)
         dx, dy = T.grid_steps(np.asarray(self.xx), np.asarray(self.yy))
         vario = self._vario_dict()
-        off, cnt, hw = T.octant_stencil(dx, dy, self.sgs_param[1])
+        # The reference widens the search radius by 100 km for a node that finds no conditioned cell (MCMC.py:149-155).
+        # Every cell outside the block is conditioned unless the bed holds NaN, so with a radius longer than the largest
+        # block edge the first level always finds data and the (much larger) tables of the wider radii are not built.
+        radius = float(self.sgs_param[1])
+        bmax = max(self.block_max_x, self.block_max_y)
+        self._sgs_levels = bool(widen) or radius / min(abs(dx), abs(dy)) <= bmax + 1
+        if self._sgs_levels:
+            off, cnt, hw, _radii = T.search_levels(dx, dy, H, W, radius)
+        else:
+            off, cnt, hw = T.octant_stencil(dx, dy, radius)
         lut = T.covariance_lut(dx, dy, hw, vario)
         trend = np.asarray(self.trend, dtype=np.float64) if self.detrend_map else None
         cond_c = np.asarray(self.cond_bed, dtype=np.float64) - (trend if trend is not None else 0.0)
@@ -713,7 +722,8 @@ class SgsBatch:
             raise GmcShapeError(f"initial beds have shape {beds.shape}, expected [C,{chain_obj.xx.shape[0]},{chain_obj.xx.shape[1]}]")
         self.C, self.H, self.W = beds.shape
         self.chain = chain_obj
-        self.ctx = chain_obj._sgs_context(self.C, device)
+        # NaN cells in the beds are unconditioned cells outside the block: a node may then find nothing within the radius
+        self.ctx = chain_obj._sgs_context(self.C, device, widen=bool(np.isnan(beds).any()))
         dev = self.dev = self.ctx.device
         full = torch.as_tensor(beds).to(dev)
         self.bedc = torch.empty_like(full)
@@ -734,8 +744,8 @@ class SgsBatch:
 
     def _check_err(self):
         if int(self.err.item()) != 0:
-            raise GmcError("SGS: a node found no conditioned neighbour inside the search radius; the reference widens the "
-                           "radius by 100 km in that case (MCMC.py:149-155), which this kernel does not implement")
+            raise GmcError("SGS: a node found no conditioned neighbour inside the search radius nor inside the widened radii "
+                           "(radius + 100 km steps, MCMC.py:149-155, up to the grid diagonal / sgs_tables.MAX_LEVELS)")
 
     def loss(self):
         den = self.torch.full_like(self.ssq, 2 * self.chain.sigma_mc ** 2)
@@ -946,12 +956,21 @@ class ChainBatch:
             self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(groups)]
         main = torch.cuda.current_stream()
         bounds = [(g * self.C) // groups for g in range(groups + 1)]
+        # debug (GMC_TRACE_PIPELINE=1): timing events per range - upload queued / kernel queued / kernel done / download done
+        trace = self._trace = [] if os.environ.get("GMC_TRACE_PIPELINE") else None
+
+        def mark(g, what):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                trace.append((g, what, ev))
         for g, strm in enumerate(self._streams):
             a, b = bounds[g], bounds[g + 1]
             if a == b:
                 continue
             strm.wait_stream(main)
             with torch.cuda.stream(strm):
+                mark(g, 0)
                 self.bed[a:b].copy_(host_beds[a:b], non_blocking=True)
                 if self.resampled is not None:
                     self.resampled[a:b].zero_()
@@ -959,14 +978,17 @@ class ChainBatch:
                 lc[a:b, 0] = self.ssq[a:b] / den
                 st[a:b, 0] = 0
                 bl[a:b, 0] = -1
+                mark(g, 1)
                 self.ctx.run(self.bed[a:b], self.mcres[a:b], self.ssq[a:b], self.seeds[a:b], iter0, n_steps, lc[a:b], st[a:b],
                              bl[a:b], 1, None if self.resampled is None else self.resampled[a:b], resync_every)
+                mark(g, 2)
                 out["bed"][a:b].copy_(self.bed[a:b], non_blocking=True)
                 out["loss"][a:b].copy_(lc[a:b], non_blocking=True)
                 out["steps"][a:b].copy_(st[a:b], non_blocking=True)
                 out["blocks"][a:b].copy_(bl[a:b], non_blocking=True)
                 if "resampled" in out:
                     out["resampled"][a:b].copy_(self.resampled[a:b], non_blocking=True)
+                mark(g, 3)
         self.iteration = int(iter0) + n_steps
         pending = PendingRun(self, out)
         return pending.wait() if wait else pending

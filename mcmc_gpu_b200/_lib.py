@@ -50,7 +50,7 @@ PROTOTYPES = {
                           C.c_int, C.c_int, _c_p]),
     "gmc_ensemble_moments": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
     "gmc_allreduce_moments": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),
-    "gmc_sgs_setup": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int, _c_p, _f64,
+    "gmc_sgs_setup": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p, _c_p, C.c_int, C.c_int, C.c_int, C.c_int, _c_p, _f64,
                                 C.c_int, C.c_int, C.c_int, C.c_int]),
     "gmc_sgs_transform": (C.c_int, [_c_p, _c_p, _c_p, _i64, C.c_int, _c_p]),
     "gmc_sgs_init": (C.c_int, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, C.c_int, _c_p]),
@@ -265,9 +265,12 @@ class Context:
         trend, zcond, quantiles, references, lut = f64(trend), f64(zcond), f64(quantiles), f64(references), f64(lut)
         grounded = np.ascontiguousarray(np.asarray(grounded) == 1, dtype=np.uint8)
         oct_off = np.ascontiguousarray(oct_off, dtype=np.int16)
-        oct_cnt = np.ascontiguousarray(oct_cnt, dtype=np.int32)
+        oct_cnt = np.ascontiguousarray(np.atleast_2d(oct_cnt), dtype=np.int32)          # [n_levels][8]
+        if oct_cnt.shape[1] != 8:
+            raise GmcShapeError(f"octant counts have shape {oct_cnt.shape}, expected [n_levels, 8]")
         check(self.lib.gmc_sgs_setup(self._h, _ptr(trend), _ptr(zcond), _ptr(grounded), _ptr(quantiles), _ptr(references),
-                                     0 if quantiles is None else quantiles.size, _ptr(oct_off), _ptr(oct_cnt), oct_off.shape[1],
+                                     0 if quantiles is None else quantiles.size, _ptr(oct_off), _ptr(oct_cnt), oct_cnt.shape[0],
+                                     oct_off.shape[1],
                                      int(hw), int(num_points), _ptr(lut), float(sill), *[int(b) for b in blocks]))
 
     def sgs_transform(self, x, out, inverse=False):

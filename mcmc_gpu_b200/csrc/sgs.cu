@@ -25,6 +25,8 @@
 #define SGS_SIG_PITCH (SGS_MAX_NEIGH + 3)   // augmented matrix [Sigma | rho | 1], odd pitch
 #define SGS_NEAR 64               // offsets per octant staged in shared memory
 
+#define SGS_MAX_LEVELS 4           // search radii radius, radius + 100 km, ... (MCMC.py:149-155, interpolate.py:149-155)
+
 struct SgsDev {
     const double* trend;          // [H][W] or nullptr
     const double* zcond;          // [H][W] normal-scored radar values, NaN where none
@@ -33,7 +35,8 @@ struct SgsDev {
     const double* refs;           // [nq] references
     int nq;
     const int16_t* oct_off;       // [8][lmax][2] (di, dj), sorted by (distance, di, dj); octant b-(-4) of neighbors.py:54
-    const int32_t* oct_cnt;       // [8]
+    const int32_t* oct_cnt;       // [n_levels][8]: prefix lengths of the lists for radius, radius + 100 km, ... (MCMC.py:149-155)
+    int n_levels;
     int lmax, hw, per_oct;        // per_oct = num_points // 8
     const double* lut;            // [(4hw+1)][(4hw+1)] covariance of the offset (di, dj)
     int lut_w;                    // 4hw+1
@@ -290,10 +293,13 @@ __device__ __forceinline__ void sgs_warp_node(const GmcDev& d, const SgsDev& s, 
     const int bi = node / bw, bj = node - bi * bw;
     const int i = x0 + bi, j = y0 + bj;
     // (a) octant search, octants in the reference's order                                       neighbors.py:52-60
+    // The lists are sorted by distance, so the offsets closer than a level's radius are a prefix: a node that finds nothing
+    // within `radius` searches again with radius + 100 km, as the reference does (MCMC.py:149-155).
     int n = 0;
+    for (int lev = 0; lev < s.n_levels && n == 0; ++lev)
     for (int o = 0; o < 8; ++o) {
         const int16_t* off = s.oct_off + (int64_t)o * s.lmax * 2;
-        const int cnt = __ldg(s.oct_cnt + o);
+        const int cnt = __ldg(s.oct_cnt + lev * 8 + o);
         int found = 0;
         for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
             const int t = base + lane;
@@ -481,9 +487,11 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
         const int bi = node / bw, bj = node - bi * bw;
         const int i = x0 + bi, j = y0 + bj;
         // (a) octant search: warp `wid` owns octant wid (b = wid - 4)                           neighbors.py:52-60
+        int lev = 0;
+    search_again:
         {
             const int16_t* off = s.oct_off + (int64_t)wid * s.lmax * 2;
-            const int cnt = __ldg(s.oct_cnt + wid);
+            const int cnt = __ldg(s.oct_cnt + lev * 8 + wid);
             int found = 0;
             for (int base = 0; base < cnt && found < s.per_oct; base += 32) {
                 const int t = base + lane;
@@ -527,7 +535,12 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
             start[o] = n;
             n += S.oct_n[o];
         }
-        if (n == 0) {                                   // the reference would widen the radius by 100 km (MCMC.py:149-155)
+        if (n == 0 && lev + 1 < s.n_levels) {           // nothing within this radius: widen by 100 km (MCMC.py:149-155)
+            ++lev;
+            __syncthreads();
+            goto search_again;
+        }
+        if (n == 0) {                                   // no conditioned cell within the widest table either
             if (tid == 0) S.err = 1;
             if (tid == 0) S.blk_z[node] = 0.0;
             __syncthreads();
@@ -946,9 +959,11 @@ static void sgs_free(gmc_sgs_state* st) {
 
 extern "C" int gmc_sgs_setup(gmc_ctx* c, const double* trend, const double* zcond, const uint8_t* grounded,
                              const double* quantiles, const double* references, int n_quantiles, const int16_t* oct_off,
-                             const int32_t* oct_cnt, int lmax, int hw, int num_points, const double* lut, double sill,
+                             const int32_t* oct_cnt, int n_levels, int lmax, int hw, int num_points, const double* lut, double sill,
                              int block_min_x, int block_max_x, int block_min_y, int block_max_y) {
     if (!c) GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: ctx is NULL");
+    if (n_levels < 1 || n_levels > SGS_MAX_LEVELS)
+        GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: n_levels=%d outside [1,%d]", n_levels, SGS_MAX_LEVELS);
     if (!c->have_static) GMC_FAIL(GMC_ESTATE, "gmc_sgs_setup: call gmc_set_static first");
     if (!zcond || !grounded || !oct_off || !oct_cnt || !lut) GMC_FAIL(GMC_EINVAL, "gmc_sgs_setup: NULL argument");
     if ((quantiles == nullptr) != (references == nullptr) || (quantiles && n_quantiles < 2))
@@ -993,8 +1008,9 @@ extern "C" int gmc_sgs_setup(gmc_ctx* c, const double* trend, const double* zcon
     }
     if ((rc = upload(oct_off, (size_t)8 * lmax * 2, &sp, &st->owned[5]))) return rc;
     s.oct_off = sp;
-    if ((rc = upload(oct_cnt, (size_t)8, &ip, &st->owned[6]))) return rc;
+    if ((rc = upload(oct_cnt, (size_t)8 * n_levels, &ip, &st->owned[6]))) return rc;
     s.oct_cnt = ip;
+    s.n_levels = n_levels;
     s.lut_w = 4 * hw + 1;
     if ((rc = upload(lut, (size_t)s.lut_w * s.lut_w, &dp, &st->owned[7]))) return rc;
     s.lut = dp;
@@ -1139,7 +1155,6 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
 //      est = mean + sum w_i (v_i - mean) over the recorded neighbours (a sparse triangular solve), the truncated-normal
 //      draw when bounds are given (interpolate.py:166-181), writing the normal-score grid in place.
 // =====================================================================================================================
-#define SGS_MAX_LEVELS 4           // search radii radius, radius + 100 km, ... (interpolate.py:149-155)
 struct SgsGridShared {
     SgsWarpRec rec[8];
     int cell[8][SGS_WN];

@@ -16,11 +16,9 @@ import numbers
 import numpy as np
 
 from .. import _lib
-from ..sgs_tables import covariance_lut, grid_steps, octant_stencil
+from ..sgs_tables import MAX_HALF_WIDTH, MAX_LEVELS, covariance_lut, grid_steps, octant_stencil, search_levels  # noqa: F401
 
 MAX_POINTS = 48
-MAX_LEVELS = 4            # search radii: radius, +100 km, +200 km, +300 km
-MAX_HALF_WIDTH = 700      # cells; bounds the offset lists and the covariance table ((4 hw + 1)^2 doubles)
 
 
 def _generator(seed):
@@ -52,23 +50,6 @@ def _sanity_checks(xx, yy, grid, vario, radius, num_points, ktype, sim_mask):
         raise ValueError("sim_mask shape must be same as grid if provided")
     if ktype not in ("ok", "sk"):
         raise ValueError("ktype must be 'ok' or 'sk'")
-
-
-def search_levels(dx, dy, H, W, radius):
-    """Octant search tables for `radius` and its widened versions: a node that finds no data within `radius` searches
-    again with radius + 100 km (interpolate.py:149-155).  The octant lists are sorted by distance, so every radius level is
-    a prefix of the lists built for the widest one; levels stop once the radius covers the grid diagonal (or after
-    MAX_LEVELS, or when the tables would get unreasonably large).
-    Returns (offsets int16 [8, lmax, 2], counts int32 [levels, 8], half-width of the widest window, radii)."""
-    diag = float(np.hypot(abs(dx) * W, abs(dy) * H))
-    radii = [float(radius)]
-    while radii[-1] < diag and len(radii) < MAX_LEVELS and (radii[-1] + 100e3) / min(abs(dx), abs(dy)) <= MAX_HALF_WIDTH:
-        radii.append(radii[-1] + 100e3)
-    off, cnt_max, hw = octant_stencil(dx, dy, radii[-1])
-    dist = np.sqrt((off[..., 1] * dx) ** 2 + (off[..., 0] * dy) ** 2)         # [8, lmax], the reference's expression
-    valid = np.arange(off.shape[1])[None, :] < cnt_max[:, None]
-    cnt = np.stack([((dist < r) & valid).sum(1) for r in radii]).astype(np.int32)   # [levels, 8]
-    return off, cnt, hw, radii
 
 
 def sgs_many(xx, yy, grid, variogram, seeds, radius=100e3, num_points=20, ktype="ok", sim_mask=None, bounds=None,

@@ -45,6 +45,27 @@ def octant_stencil(dx, dy, radius):
     return off, cnt, hw
 
 
+MAX_LEVELS = 4            # search radii: radius, +100 km, +200 km, +300 km
+MAX_HALF_WIDTH = 700      # cells; bounds the offset lists and the covariance table ((4 hw + 1)^2 doubles)
+
+
+def search_levels(dx, dy, H, W, radius):
+    """Octant search tables for `radius` and its widened versions: a node that finds no data within `radius` searches
+    again with radius + 100 km (interpolate.py:149-155).  The octant lists are sorted by distance, so every radius level is
+    a prefix of the lists built for the widest one; levels stop once the radius covers the grid diagonal (or after
+    MAX_LEVELS, or when the tables would get unreasonably large).
+    Returns (offsets int16 [8, lmax, 2], counts int32 [levels, 8], half-width of the widest window, radii)."""
+    diag = float(np.hypot(abs(dx) * W, abs(dy) * H))
+    radii = [float(radius)]
+    while radii[-1] < diag and len(radii) < MAX_LEVELS and (radii[-1] + 100e3) / min(abs(dx), abs(dy)) <= MAX_HALF_WIDTH:
+        radii.append(radii[-1] + 100e3)
+    off, cnt_max, hw = octant_stencil(dx, dy, radii[-1])
+    dist = np.sqrt((off[..., 1] * dx) ** 2 + (off[..., 0] * dy) ** 2)         # [8, lmax], the reference's expression
+    valid = np.arange(off.shape[1])[None, :] < cnt_max[:, None]
+    cnt = np.stack([((dist < r) & valid).sum(1) for r in radii]).astype(np.int32)   # [levels, 8]
+    return off, cnt, hw, radii
+
+
 def covariance_model(vtype, h, sill, nugget, s=None):
     """Covariance of the range-normalised lag h (covariance.py:4-22), including the spherical model's quirk."""
     h = np.array(h, dtype=np.float64, copy=True)
