@@ -23,6 +23,10 @@ import sys
 import threading
 import time
 
+# the end-to-end pipeline keeps (steps in flight) x (chain ranges) x 2 CUDA streams busy; with the default 8 hardware queues
+# unrelated streams share a queue and serialise behind each other's 40 ms kernels
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -478,7 +482,8 @@ def gpu_main(a):
     g, ch, rf = build_chain(MCMC, syn, H, W, quiet)
     seeds = [1000 + chain0 + c for c in range(C)]                   # global chain id -> seed: invariant to GPU count
     n_it = a.iters
-    NBUF = int(os.environ.get("GMC_E2E_STEPS_IN_FLIGHT", "3"))      # e2e: steps in flight (multi-buffered device state)
+    NBUF = int(os.environ.get("GMC_E2E_STEPS_IN_FLIGHT", "2"))      # e2e: steps in flight (multi-buffered device state)
+    E2E_RANGES = int(os.environ.get("GMC_E2E_RANGES", "8"))         # chain ranges per step (two streams each)
 
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype).pin_memory()
@@ -562,7 +567,8 @@ def gpu_main(a):
             b = k % NBUF if overlap else 0
             if pend[b] is not None:
                 pend[b].wait()
-            pend[b] = ch.run_many(n_it + 1, rf, host_beds, seeds, as_arrays=True, batch=batches[b], out=outs[b], wait=False)
+            pend[b] = ch.run_many(n_it + 1, rf, host_beds, seeds, as_arrays=True, batch=batches[b], out=outs[b], wait=False,
+                                  pipeline_groups=E2E_RANGES if overlap else 16)
             if not overlap:
                 pend[b].wait()
                 pend[b] = None
@@ -647,7 +653,7 @@ def gpu_main(a):
                 "scaling": "strong" if a.chains_total else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg, "details": {"acceptance_rate": acc_rate, "step_kernel": info, "cpu_affinity": affinity},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / a.steps, "steps_in_flight": NBUF,
+                        "ms_per_step": e2e_ms / a.steps, "steps_in_flight": NBUF, "chain_ranges_per_step": E2E_RANGES,
                         "serial": {"value": total_chains * n_it * a.steps / (e2e_serial_ms * 1e-3), "ms_per_step": e2e_serial_ms / a.steps,
                                    "what": "one step at a time (upload, compute and download of a step finish before the next starts)"},
                         "host_bandwidth": hostbw,

@@ -953,7 +953,19 @@ class ChainBatch:
         den = torch.full((1,), 2 * self.chain.sigma_mc ** 2, dtype=torch.float64, device=self.dev)
         groups = max(1, min(int(groups), self.C))
         if not hasattr(self, "_streams") or len(self._streams) != groups:
-            self._streams = [torch.cuda.Stream(device=self.dev) for _ in range(groups)]
+            # Two streams per range.  The step kernels of the steps in flight fill every SM's register file, so the small
+            # kernels in front of a range's step kernel (zeroing, the residual stencil of the uploaded beds, the row-0
+            # fills) can only run in slots that a retiring step CTA frees; on HIGH-priority streams they are dispatched
+            # before the pending step CTAs of other ranges, so the next step's kernels are ready long before the current
+            # step ends (measured with GMC_TRACE_PIPELINE: without priorities they became ready 48 ms after their upload
+            # was queued and the pipeline ran at 48.6 ms per step instead of ~40).
+            lo, hi = 0, 0
+            try:
+                lo, hi = torch.cuda.Stream.priority_range()          # (least, greatest): e.g. (0, -5)
+            except Exception:
+                pass
+            self._streams = [torch.cuda.Stream(device=self.dev, priority=lo) for _ in range(groups)]
+            self._pre_streams = [torch.cuda.Stream(device=self.dev, priority=hi) for _ in range(groups)]
         main = torch.cuda.current_stream()
         bounds = [(g * self.C) // groups for g in range(groups + 1)]
         # debug (GMC_TRACE_PIPELINE=1): timing events per range - upload queued / kernel queued / kernel done / download done
@@ -968,8 +980,9 @@ class ChainBatch:
             a, b = bounds[g], bounds[g + 1]
             if a == b:
                 continue
-            strm.wait_stream(main)
-            with torch.cuda.stream(strm):
+            pre = self._pre_streams[g]
+            pre.wait_stream(main)
+            with torch.cuda.stream(pre):
                 mark(g, 0)
                 self.bed[a:b].copy_(host_beds[a:b], non_blocking=True)
                 if self.resampled is not None:
@@ -979,6 +992,8 @@ class ChainBatch:
                 st[a:b, 0] = 0
                 bl[a:b, 0] = -1
                 mark(g, 1)
+            strm.wait_stream(pre)
+            with torch.cuda.stream(strm):
                 self.ctx.run(self.bed[a:b], self.mcres[a:b], self.ssq[a:b], self.seeds[a:b], iter0, n_steps, lc[a:b], st[a:b],
                              bl[a:b], 1, None if self.resampled is None else self.resampled[a:b], resync_every)
                 mark(g, 2)

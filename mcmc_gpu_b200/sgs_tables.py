@@ -21,11 +21,14 @@ def grid_steps(xx, yy):
     return dx, dy
 
 
-def octant_stencil(dx, dy, radius):
+def octant_stencil(dx, dy, radius, hw_cap=None):
     """For octant b = -4..3 (neighbors.py:52-60) the window offsets (di, dj) with distance < radius, ordered by
     (distance, di, dj) — i.e. np.argsort(kind='stable') over the row-major window, which is how ties are broken.
+    hw_cap bounds the window half width (offsets that can never fall inside the grid need not be listed).
     Returns (offsets int16 [8, lmax, 2], counts int32 [8], hw)."""
     hw = math.ceil(radius / abs(dx))                       # make_circle_stencil: ncells = ceil(rad/dx) (neighbors.py:77-79)
+    if hw_cap is not None:
+        hw = max(1, min(hw, int(hw_cap)))
     di, dj = np.meshgrid(np.arange(-hw, hw + 1), np.arange(-hw, hw + 1), indexing="ij")
     # reference: distances = sqrt((x0 - x)^2 + (y0 - y)^2), angles = arctan2(y0 - y, x0 - x)   (neighbors.py:48-49)
     ddx, ddy = 0.0 - dj * dx, 0.0 - di * dy      # x0 - x with x0 = 0: keeps +0.0 (arctan2(-0.0, -1) would be -pi, not +pi)
@@ -59,7 +62,7 @@ def search_levels(dx, dy, H, W, radius):
     radii = [float(radius)]
     while radii[-1] < diag and len(radii) < MAX_LEVELS and (radii[-1] + 100e3) / min(abs(dx), abs(dy)) <= MAX_HALF_WIDTH:
         radii.append(radii[-1] + 100e3)
-    off, cnt_max, hw = octant_stencil(dx, dy, radii[-1])
+    off, cnt_max, hw = octant_stencil(dx, dy, radii[-1], hw_cap=max(H, W) - 1 if len(radii) > 1 else None)
     dist = np.sqrt((off[..., 1] * dx) ** 2 + (off[..., 0] * dy) ** 2)         # [8, lmax], the reference's expression
     valid = np.arange(off.shape[1])[None, :] < cnt_max[:, None]
     cnt = np.stack([((dist < r) & valid).sum(1) for r in radii]).astype(np.int32)   # [levels, 8]

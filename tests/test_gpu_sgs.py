@@ -1,5 +1,7 @@
 """K6 parity: the small-scale (SGS) chain on the GPU vs the oracle (stable tie order, the kernel's rule): normal-score
 transform, replayed trajectories (accept flags identical, loss/bed <= 1e-9), batch invariance of the free-running kernel."""
+import os
+
 import numpy as np
 import pytest
 
@@ -131,3 +133,29 @@ def test_more_chains_than_resident_ctas_is_bit_identical_to_the_static_schedule(
     lb, sb, bb = b.advance(9)
     assert bits_equal(a.beds(), b.beds()) and np.array_equal(sa, sb) and np.array_equal(ba, bb) and bits_equal(la, lb)
     assert np.isfinite(la).all()
+
+
+def test_search_radius_is_widened_in_the_chain_like_the_reference():
+    """MCMC.py:149-155: a node that finds no conditioned cell within the radius searches again 100 km wider.  With a radius
+    of 3 cells and blocks of up to 13 cells the first nodes of most paths see nothing at level 0; the replayed oracle
+    trajectory (which widens exactly like the reference) must be reproduced, with both solvers."""
+    case = dict(H=40, W=44, n_iter=14, seed=5, sigma_mc=1.5, blocks=(8, 14, 8, 14), neighbors=16, radius=1.5e3,
+                vario=dict(vtype="Matern", range=3000.0, sill=1.0, nugget=0.0, isotropic=True, smoothness=1.2259, azimuth=None),
+                transform=True, detrend=True, n_quantiles=300)
+    g, su = oracle_sgs_setup(case)
+    ora = S.sgs_chain_run(su, g["bed_init"], case["n_iter"], np.random.default_rng(case["seed"]), record=True)
+    for solver in ("warp", "cta"):
+        if solver == "cta":
+            os.environ["GMC_SGS_SOLVER"] = "cta"
+        try:
+            ch, _ = product_sgs_chain(case, g)
+            assert ch._sgs_context(1)._h is not None and ch._sgs_levels          # the widened tables were built
+            ch._ctx = None
+            out = quiet(ch.run, case["n_iter"], only_save_last_bed=True, plot=False, progress_bar=False, replay=ora["tape"])
+        finally:
+            os.environ.pop("GMC_SGS_SOLVER", None)
+        bed, _, _, loss, steps, resampled, blocks = out
+        assert np.array_equal(steps, ora["steps"]) and np.array_equal(blocks, ora["blocks"])
+        fin = np.isfinite(ora["loss"])
+        assert (np.abs(loss[fin] - ora["loss"][fin]) <= TOL * np.abs(ora["loss"][fin])).all()
+        assert np.abs(bed - ora["bed"]).max() <= TOL * np.abs(ora["bed"]).max()
