@@ -483,7 +483,7 @@ def gpu_main(a):
     seeds = [1000 + chain0 + c for c in range(C)]                   # global chain id -> seed: invariant to GPU count
     n_it = a.iters
     NBUF = int(os.environ.get("GMC_E2E_STEPS_IN_FLIGHT", "2"))      # e2e: steps in flight (multi-buffered device state)
-    E2E_RANGES = int(os.environ.get("GMC_E2E_RANGES", "8"))         # chain ranges per step (two streams each)
+    E2E_RANGES = int(os.environ.get("GMC_E2E_RANGES", "16"))        # chain ranges per step (two streams each)
 
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype).pin_memory()
@@ -506,7 +506,7 @@ def gpu_main(a):
     sampler.start()                                  # started before the warm-up: no idle gap in front of the timed region
     n_pre = 0
     t_w0 = time.perf_counter()
-    while time.perf_counter() - t_w0 < 1.5:
+    while time.perf_counter() - t_w0 < float(os.environ.get("GMC_BENCH_PREWARM_S", "1.5")):     # 0 for ncu launch lists
         batch.advance(n_it, want_caches=False)
         torch.cuda.synchronize()
         n_pre += 1

@@ -722,6 +722,23 @@ class SgsBatch:
             raise GmcShapeError(f"initial beds have shape {beds.shape}, expected [C,{chain_obj.xx.shape[0]},{chain_obj.xx.shape[1]}]")
         self.C, self.H, self.W = beds.shape
         self.chain = chain_obj
+        # Precondition of the resident-normal-score formulation: the reference maps the WHOLE grid through
+        # inverse_transform(transform(.)) on every proposal (MCMC.py:1767,1777), which clamps every detrended cell outside
+        # the transformer's fitted range [quantiles_[0], quantiles_[-1]] from its first accepted step on; this kernel
+        # round-trips only the accepted block.  The two agree (to the transform's own <= 1e-12 round-trip drift) exactly
+        # when no detrended cell lies outside that range - true for a transformer fitted on initial_bed - trend as in the
+        # reference's scripts, not for one fitted on the conditioning data alone.
+        if getattr(chain_obj, "do_transform", False) and getattr(chain_obj, "nst_trans", None) is not None:
+            q = np.asarray(chain_obj.nst_trans.quantiles_[:, 0], dtype=np.float64)
+            base = beds - (np.asarray(chain_obj.trend, dtype=np.float64)[None] if chain_obj.detrend_map else 0.0)
+            n_out = int(np.count_nonzero((base < q[0]) | (base > q[-1])))
+            if n_out:
+                import warnings
+                warnings.warn(f"chain_sgs: {n_out} detrended bed cells lie outside the normal-score transformer's fitted range "
+                              f"[{q[0]:.6g}, {q[-1]:.6g}]; the reference clamps such cells to that range at its first accepted "
+                              "step (MCMC.py:1767-1806) while this kernel leaves cells outside the proposed blocks untouched, "
+                              "so the trajectories differ there.  Fit the transformer on initial_bed - trend (as the reference's "
+                              "drivers do) or clip the initial beds to the fitted range.", RuntimeWarning, stacklevel=3)
         # NaN cells in the beds are unconditioned cells outside the block: a node may then find nothing within the radius
         self.ctx = chain_obj._sgs_context(self.C, device, widen=bool(np.isnan(beds).any()))
         dev = self.dev = self.ctx.device
@@ -897,6 +914,7 @@ class ChainBatch:
 
     def advance(self, n_steps, resync_every=4096, want_caches=True):
         """n_steps fused free-running iterations (kernel K1+K4).  Returns (loss[C,n], accepted[C,n], blocks[C,n,4])."""
+        self.ctx.set_step_cta("auto")
         lc = st = bl = None
         if want_caches:
             lc, st, bl = self._device_caches(n_steps)
@@ -914,6 +932,7 @@ class ChainBatch:
         as stacked arrays; results land in the pinned tensors of `out` when given (one D2H copy each)."""
         torch = self.torch
         n = n_steps + 1
+        self.ctx.set_step_cta("auto")
         lc, st, bl = self._device_caches(n)
         lc[:, 0] = self._loss_now()
         st[:, 0] = 0
@@ -968,6 +987,9 @@ class ChainBatch:
             self._pre_streams = [torch.cuda.Stream(device=self.dev, priority=hi) for _ in range(groups)]
         main = torch.cuda.current_stream()
         bounds = [(g * self.C) // groups for g in range(groups + 1)]
+        # several launches share the GPU (chain ranges, or further steps in flight when wait=False): 512-thread CTAs of
+        # different launches cannot co-reside on an SM, so keep the 256-thread step kernel
+        self.ctx.set_step_cta("narrow" if (groups > 1 or not wait) else "auto")
         # debug (GMC_TRACE_PIPELINE=1): timing events per range - upload queued / kernel queued / kernel done / download done
         trace = self._trace = [] if os.environ.get("GMC_TRACE_PIPELINE") else None
 

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "gmc_launch_count": (_i64, [_c_p]),
     "gmc_step_kernel_info": (C.c_int, [_c_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gmc_check": (C.c_int, [_c_p, C.c_int]),
+    "gmc_set_step_cta": (C.c_int, [_c_p, C.c_int]),
     "gmc_debug_fp64_peak": (C.c_int, [_c_p, C.POINTER(_f64)]),
     "gmc_debug_phase_timing": (C.c_int, [_c_p, C.c_int, _c_p]),
     "gmc_debug_div_check": (C.c_int, [_c_p, _c_p, _i64, _f64, C.POINTER(_i64)]),
@@ -324,13 +325,18 @@ class Context:
         if n_chains is not None:
             import torch
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-            wide = n_chains <= sms
+            wide = n_chains <= sms and getattr(self, "_cta_mode", 0) != 1
             env = os.environ.get("GMC_STEP_WIDE")
             if env is not None:
                 wide = env[:1] == "1" and n_chains <= c.value * sms
             if wide:
                 info.update(threads=512, ctas_per_sm=1)
         return info
+
+    def set_step_cta(self, mode):
+        """'auto' | 'narrow' | 'wide' (gmc_set_step_cta): callers whose launches share the GPU select 'narrow'."""
+        self._cta_mode = {"auto": 0, "narrow": 1, "wide": 2}[mode]
+        check(self.lib.gmc_set_step_cta(self._h, self._cta_mode))
 
     def check(self):
         """Synchronise and raise GmcError if a kernel gave up a bounded in-kernel wait (chain state of that launch invalid)."""

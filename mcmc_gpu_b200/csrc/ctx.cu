@@ -76,6 +76,7 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     }
     c->h_err = c->d_err = nullptr;
     c->step_wide_ctas = 0;
+    c->step_cta_mode = 0;
     c->spin_limit = 1u << 26;
     if (const char* e = getenv("GMC_DEBUG_SPIN_LIMIT")) c->spin_limit = (unsigned)strtoul(e, nullptr, 10);
     if (cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
@@ -465,6 +466,17 @@ extern "C" int gmc_check(gmc_ctx* c, int synchronize) {
         GMC_CUDA(cudaDeviceSynchronize());
     }
     return gmc_check_device_error(c, "gmc_check");
+}
+
+// CTA size of the fused step kernel.  Auto gives a launch with no more chains than SMs 512-thread CTAs (one per SM); that
+// is right when the launch has the GPU to itself and wrong when several launches share it (chain ranges on different
+// streams, several steps in flight): their 512-thread CTAs cannot co-reside and the launches serialise.  Such callers
+// select mode 1.
+extern "C" int gmc_set_step_cta(gmc_ctx* c, int mode) {
+    if (!c) GMC_FAIL(GMC_EINVAL, "gmc_set_step_cta: ctx is NULL");
+    if (mode < 0 || mode > 2) GMC_FAIL(GMC_EINVAL, "gmc_set_step_cta: mode %d outside {0 auto, 1 narrow, 2 wide}", mode);
+    c->step_cta_mode = mode;
+    return GMC_OK;
 }
 
 extern "C" int gmc_step_kernel_info(const gmc_ctx* c, int* smem_bytes, int* threads, int* ctas_per_sm) {

@@ -210,6 +210,8 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
     // of 256 - the step is latency bound and a lone 256-thread CTA leaves half of the SM's issue slots idle
     static const char* wide_env = getenv("GMC_STEP_WIDE");            // "0" / "1" force the choice (A/B runs)
     bool wide = !sched && c->step_wide_ctas >= 1 && C <= c->sm_count;
+    if (c->step_cta_mode == 1) wide = false;                           // gmc_set_step_cta: the launch shares the GPU
+    if (c->step_cta_mode == 2) wide = !sched && c->step_wide_ctas >= 1;
     if (wide_env) wide = !sched && c->step_wide_ctas >= 1 && wide_env[0] == '1';
     if (wide)
         t512::run_kernel<<<grid, 512, c->step_smem_bytes, st>>>(

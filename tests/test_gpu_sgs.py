@@ -159,3 +159,20 @@ def test_search_radius_is_widened_in_the_chain_like_the_reference():
         fin = np.isfinite(ora["loss"])
         assert (np.abs(loss[fin] - ora["loss"][fin]) <= TOL * np.abs(ora["loss"][fin])).all()
         assert np.abs(bed - ora["bed"]).max() <= TOL * np.abs(ora["bed"]).max()
+
+
+def test_out_of_range_cells_are_reported():
+    """cells outside the transformer's fitted range are where the block-local round trip and the reference's
+    whole-grid round trip part ways; the batch constructor says so instead of diverging silently."""
+    from mcmc_gpu_b200 import MCMC
+    case = SGS_CASES["matern_nst"]
+    ch, g = product_sgs_chain(case)
+    bed = g["bed_init"].copy()
+    import warnings
+    with warnings.catch_warnings(record=True) as rec:                # in range: no warning
+        warnings.simplefilter("always")
+        MCMC.SgsBatch(ch, bed[None], [1])
+    assert not [w for w in rec if issubclass(w.category, RuntimeWarning)]
+    bed[3, 4] += 1e4                                                 # far above the largest fitted quantile
+    with pytest.warns(RuntimeWarning, match="outside the normal-score transformer's fitted range"):
+        MCMC.SgsBatch(ch, bed[None], [1])
