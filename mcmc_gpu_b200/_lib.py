@@ -325,17 +325,25 @@ class Context:
         if n_chains is not None:
             import torch
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-            wide = n_chains <= sms and getattr(self, "_cta_mode", 0) != 1
-            env = os.environ.get("GMC_STEP_WIDE")
-            if env is not None:
-                wide = env[:1] == "1" and n_chains <= c.value * sms
-            if wide:
-                info.update(threads=512, ctas_per_sm=1)
+            slots = c.value * sms
+            mode = getattr(self, "_cta_mode", 0)
+            split = (mode in (0, 3)) and 2 * n_chains <= slots
+            if os.environ.get("GMC_STEP_SPLIT") is not None:
+                split = os.environ["GMC_STEP_SPLIT"][:1] == "1" and 2 * n_chains <= slots
+            wide = (not split) and ((mode == 0 and n_chains <= sms) or mode == 2)
+            if os.environ.get("GMC_STEP_WIDE") is not None:
+                wide = (not split) and os.environ["GMC_STEP_WIDE"][:1] == "1" and n_chains <= slots
+            if split:
+                info.update(mode="split: field producer CTA + Metropolis tail CTA per chain", ctas_per_chain=2)
+            elif wide:
+                info.update(threads=512, ctas_per_sm=1, mode="wide")
+            else:
+                info.update(mode="fused")
         return info
 
     def set_step_cta(self, mode):
-        """'auto' | 'narrow' | 'wide' (gmc_set_step_cta): callers whose launches share the GPU select 'narrow'."""
-        self._cta_mode = {"auto": 0, "narrow": 1, "wide": 2}[mode]
+        """'auto' | 'narrow' | 'wide' | 'split' (gmc_set_step_cta): callers whose launches share the GPU select 'narrow'."""
+        self._cta_mode = {"auto": 0, "narrow": 1, "wide": 2, "split": 3}[mode]
         check(self.lib.gmc_set_step_cta(self._h, self._cta_mode))
 
     def check(self):

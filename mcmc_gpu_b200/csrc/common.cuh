@@ -148,6 +148,11 @@ struct gmc_ctx {
     int* d_err;            // device alias of h_err
     unsigned spin_limit;   // bound of the in-kernel waits (GMC_DEBUG_SPIN_LIMIT overrides the default 2^26)
     int step_wide_ctas;    // occupancy of the 512-thread step kernel (0 = unavailable)
+    double* d_ring;        // split mode: ring of proposal fields [C][depth][max_h * max_w] written by the producer CTAs
+    size_t ring_bytes;
+    int* d_pflags;         // split mode: [max_chains][2] fields produced / consumed in the current launch
+    cudaStream_t aux_stream;   // split mode: the producer kernel runs here, fenced to the caller's stream by two events
+    cudaEvent_t ev_fork, ev_join;
     int step_cta_mode;     // gmc_set_step_cta: 0 auto (512 threads when C <= SMs), 1 always 256 threads, 2 512 threads when it fits
     gmc_sgs_state* sgs;    // small-scale (SGS) chain tables, see sgs.cu
 };

@@ -77,6 +77,11 @@ extern "C" int gmc_create(gmc_ctx** out, int device, int H, int W, int max_chain
     c->h_err = c->d_err = nullptr;
     c->step_wide_ctas = 0;
     c->step_cta_mode = 0;
+    c->d_ring = nullptr;
+    c->ring_bytes = 0;
+    c->d_pflags = nullptr;
+    c->aux_stream = nullptr;
+    c->ev_fork = c->ev_join = nullptr;
     c->spin_limit = 1u << 26;
     if (const char* e = getenv("GMC_DEBUG_SPIN_LIMIT")) c->spin_limit = (unsigned)strtoul(e, nullptr, 10);
     if (cudaHostAlloc((void**)&c->h_err, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
@@ -113,6 +118,11 @@ extern "C" int gmc_destroy(gmc_ctx* c) {
     for (int k = 0; k < GMC_SCHED_SLOTS; ++k)
         if (c->sched_ev[k]) cudaEventDestroy(c->sched_ev[k]);
     if (c->h_err) cudaFreeHost(c->h_err);
+    cudaFree(c->d_ring);
+    cudaFree(c->d_pflags);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     gmc_sgs_destroy(c);
     delete c;
     return GMC_OK;
@@ -474,7 +484,7 @@ extern "C" int gmc_check(gmc_ctx* c, int synchronize) {
 // select mode 1.
 extern "C" int gmc_set_step_cta(gmc_ctx* c, int mode) {
     if (!c) GMC_FAIL(GMC_EINVAL, "gmc_set_step_cta: ctx is NULL");
-    if (mode < 0 || mode > 2) GMC_FAIL(GMC_EINVAL, "gmc_set_step_cta: mode %d outside {0 auto, 1 narrow, 2 wide}", mode);
+    if (mode < 0 || mode > 3) GMC_FAIL(GMC_EINVAL, "gmc_set_step_cta: mode %d outside {0 auto, 1 narrow, 2 wide, 3 split}", mode);
     c->step_cta_mode = mode;
     return GMC_OK;
 }

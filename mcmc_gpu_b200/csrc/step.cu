@@ -76,6 +76,8 @@ int gmc_step_configure(gmc_ctx* c) {
     GMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, run_kernel, GMC_STEP_THREADS, need));
     c->step_ctas_per_sm = nb;
     // the 512-thread variant (one CTA per SM) for launches with no more chains than SMs
+    GMC_CUDA(cudaFuncSetAttribute(tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+    GMC_CUDA(cudaFuncSetAttribute(field_producer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fmax));
     c->step_wide_ctas = 0;
     if (cudaFuncSetAttribute(t512::run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need) == cudaSuccess) {
         int nw = 0;
@@ -206,13 +208,49 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
         // predecessor chunk (bounded spin in the kernel) in the millisecond range however long the launch is
         chunk = std::min(256, std::max(4, (n_steps + 31) / 32));
     }
-    // no more chains than SMs: every CTA is alone on its SM either way, so give each chain 512 threads (16 warps) instead
-    // of 256 - the step is latency bound and a lone 256-thread CTA leaves half of the SM's issue slots idle
-    static const char* wide_env = getenv("GMC_STEP_WIDE");            // "0" / "1" force the choice (A/B runs)
-    bool wide = !sched && c->step_wide_ctas >= 1 && C <= c->sm_count;
-    if (c->step_cta_mode == 1) wide = false;                           // gmc_set_step_cta: the launch shares the GPU
+    // Launches that under-fill the GPU (auto mode; gmc_set_step_cta(1) = "this launch shares the GPU" disables both):
+    //  * at most half as many chains as CTA slots: SPLIT mode - a producer CTA synthesises the fields of the coming steps
+    //    while the consumer CTA of the same chain runs the Metropolis tail (two kernels, the producer on the context's
+    //    auxiliary stream, fenced to the caller's stream by events);
+    //  * else no more chains than SMs: 512-thread CTAs, one per SM.
+    static const char* wide_env = getenv("GMC_STEP_WIDE");            // "0" / "1" force the 512-thread choice (A/B runs)
+    static const char* split_env = getenv("GMC_STEP_SPLIT");          // "0" / "1" force the split choice (A/B runs)
+    bool split = !sched && c->step_cta_mode == 0 && 2 * C <= slots && n_steps >= 4;
+    if (c->step_cta_mode == 3) split = !sched && 2 * C <= slots;
+    if (split_env) split = !sched && 2 * C <= slots && split_env[0] == '1';
+    bool wide = !split && !sched && c->step_wide_ctas >= 1 && C <= c->sm_count;
+    if (c->step_cta_mode == 1 || c->step_cta_mode == 3) wide = false;  // gmc_set_step_cta: the launch shares the GPU / split only
     if (c->step_cta_mode == 2) wide = !sched && c->step_wide_ctas >= 1;
-    if (wide_env) wide = !sched && c->step_wide_ctas >= 1 && wide_env[0] == '1';
+    if (wide_env) wide = !split && !sched && c->step_wide_ctas >= 1 && wide_env[0] == '1';
+    if (split) {
+        const int depth = 3;
+        const int64_t fstride = (int64_t)c->max_h * c->max_w;
+        const size_t need_ring = (size_t)C * depth * fstride * sizeof(double);
+        if (need_ring > c->ring_bytes) {
+            cudaFree(c->d_ring);
+            c->d_ring = nullptr;
+            c->ring_bytes = 0;
+            GMC_CUDA(cudaMalloc(&c->d_ring, need_ring));
+            c->ring_bytes = need_ring;
+        }
+        if (!c->d_pflags) GMC_CUDA(cudaMalloc(&c->d_pflags, (size_t)2 * c->max_chains * sizeof(int)));
+        if (!c->aux_stream) GMC_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        if (!c->ev_fork) GMC_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        if (!c->ev_join) GMC_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        GMC_CUDA(cudaMemsetAsync(c->d_pflags, 0, (size_t)2 * C * sizeof(int), st));
+        GMC_CUDA(cudaEventRecord(c->ev_fork, st));
+        GMC_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        field_producer_kernel<<<C, GMC_STEP_THREADS, (size_t)c->step_tile_off * sizeof(double), c->aux_stream>>>(
+            c->dev, seeds, iter0, n_steps, c->d_ring, fstride, depth, c->d_pflags, c->d_err, c->spin_limit);
+        tail_kernel<<<C, GMC_STEP_THREADS, c->step_smem_bytes, st>>>(
+            c->dev, bed, mcres, ssq, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride, cache_offset, resampled,
+            resync_every, c->step_tile_off, c->d_ring, fstride, depth, c->d_pflags, c->d_err, c->spin_limit);
+        GMC_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+        GMC_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
+        c->launches += 2;
+        GMC_CUDA(cudaGetLastError());
+        return GMC_OK;
+    }
     if (wide)
         t512::run_kernel<<<grid, 512, c->step_smem_bytes, st>>>(
             c->dev, bed, mcres, ssq, seeds, iter0, n_steps, loss_cache, step_cache, blocks_cache, cache_stride, cache_offset, resampled,

@@ -776,7 +776,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
                           int f_pitch, const Philox& rng, uint32_t it_lo, uint32_t it_hi, double* tile, double* newres,
                           double* bed, double* mcres, double& ssq, int32_t* resampled, double* loss_next_out,
                           PhaseClock& pc, const NextStep* next = nullptr, uint64_t* tile_bar = nullptr, unsigned tile_parity = 0,
-                          int* err = nullptr) {
+                          int* err = nullptr, int* consumed_flag = nullptr, int consumed_val = 0) {
     const int H = d.H, W = d.W;
     const StepScalars s = *sc;
     const int bh = s.x1 - s.x0, bw = s.y1 - s.y0;
@@ -832,7 +832,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
                     const int bj = lane + 32 * c;
                     if (bj < bw && (fl[r][c] & FLAG_GATE)) {
                         double pv;
-                        if (INJECT_F) pv = f_inj[fy * f_pitch + s.my0 + bj];
+                        if (INJECT_F) pv = __ldcg(f_inj + fy * f_pitch + s.my0 + bj);      // L2: a producer CTA may have written it
                         else {
                             pv = field_value<false>(fv, fy, s.my0 + bj, rng, it_lo, it_hi);
                             if (use_taper) pv = mul_rn(pv, tpv[r][c]);                     // MCMC.py:778
@@ -846,7 +846,7 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
                     const int64_t idx = (int64_t)(s.x0 + bi) * W + s.y0 + bj;
                     if (__ldg(d.flags + idx) & FLAG_GATE) {
                         double pv;
-                        if (INJECT_F) pv = f_inj[fy * f_pitch + s.my0 + bj];
+                        if (INJECT_F) pv = __ldcg(f_inj + fy * f_pitch + s.my0 + bj);
                         else {
                             pv = field_value<false>(fv, fy, s.my0 + bj, rng, it_lo, it_hi);
                             if (use_taper) pv = mul_rn(pv, __ldg(fv.taper + fy * fv.w + s.my0 + bj));
@@ -859,6 +859,8 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
         }
     }
     __syncthreads();
+    // split mode (tail_kernel): every thread has read its cells of the injected field - its ring slot may be refilled
+    if (consumed_flag && threadIdx.x == 0) atomicExch(consumed_flag, consumed_val);
     pc.mark(5);
 
     // phase B: residual on the block, loss delta, thickness guard                       MCMC.py:1292-1329
@@ -1115,6 +1117,125 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
 }
 
 #ifndef GMC_STEP_RUN_ONLY   // the replay / field / randomization-method kernels exist for the default CTA size only
+// ---------------------------------------------------------------------------------------------------------------
+// Split mode: TWO CTAs per chain, pipelined across steps.  Nothing a field needs depends on the chain state (Philox is
+// counter addressed), so a PRODUCER CTA synthesises the tapered proposal fields of steps k, k+1, ... into a small ring in
+// global memory (L2 resident: depth x max block doubles per chain) while the CONSUMER CTA runs the Metropolis tail of step
+// k on the field it finds there (the injected-field instantiation of step_tail).  A chain then advances at the pace of the
+// slower half (~half a fused step) instead of their sum - used when a launch has at most half as many chains as the GPU has
+// CTA slots, i.e. exactly when one CTA per chain leaves the GPU under-filled.  Same arithmetic in the same order as
+// run_kernel: bit-identical trajectories (tests/test_gpu_fullsize.py).  flags[2c] = fields produced, flags[2c+1] = fields
+// consumed by chain c in this launch; both sides only ever wait for a resident CTA, with a bound (error flag, no hang).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_wait(volatile int* flag, int need, int* err, unsigned spin_limit) {
+    unsigned spins = 0;
+    while (*flag < need) {
+        __nanosleep(100);
+        if (++spins > spin_limit) {
+            *(volatile int*)err = GMC_DEVERR_WAIT_TIMEOUT;
+            __threadfence_system();
+            break;
+        }
+    }
+    __threadfence();
+}
+
+__global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
+    field_producer_kernel(GmcDev d, const uint64_t* __restrict__ seeds, uint64_t iter0, int n_steps, double* ring, int64_t fstride,
+                          int depth, int* flags, int* err, unsigned spin_limit) {
+    __shared__ double scratch[40];
+    __shared__ StepScalars sc;
+    __shared__ GmcPair s_pair;
+    __shared__ StepTables s_tab;
+    double* buf = reinterpret_cast<double*>(gmc_smem);
+    const int c = blockIdx.x;
+    const Philox rng(seeds[c]);
+    PhaseClock pc;
+    pc.acc = nullptr;
+    if (threadIdx.x < 32) prepare_step(d, rng, iter0, sc, s_pair, s_tab, false);
+    __syncthreads();
+    for (int k = 0; k < n_steps; ++k) {
+        const uint64_t it = iter0 + (uint64_t)k;
+        const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
+        const FieldView fv = synth_field<false>(d, buf, scratch, s_pair, s_tab, sc.scale, sc.nug, sc.spec, rng, it_lo, it_hi, nullptr,
+                                                nullptr, nullptr, true, pc);
+        const int h = s_pair.h, w = s_pair.w;                 // in registers: warp 0 overwrites the records below
+        // the slot of step k was last used by step k - depth: wait until the consumer has read that field
+        if (threadIdx.x == 32 && k >= depth) split_wait(flags + 2 * c + 1, k - depth + 1, err, spin_limit);
+        __syncthreads();
+        // warp 0 prepares step k+1 (scalars, block record, tables - those of step k are dead after the row pass) while the
+        // other warps write the field out; it joins them for its own share afterwards
+        if (threadIdx.x < 32 && k + 1 < n_steps) prepare_step(d, rng, it + 1, sc, s_pair, s_tab, false);
+        double* slot = ring + ((int64_t)c * depth + (k % depth)) * fstride;
+        const FastDiv dw(w);
+        for (int e = threadIdx.x; e < h * w; e += GMC_STEP_THREADS) {
+            const int y = dw.div(e), x = e - y * w;
+            double f = field_value<false>(fv, y, x, rng, it_lo, it_hi);
+            if (fv.taper) f = mul_rn(f, __ldg(fv.taper + e));                               // MCMC.py:778
+            __stcg(slot + e, f);
+        }
+        __threadfence();                                      // this thread's field values are visible device-wide ...
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(flags + 2 * c, k + 1);   // ... before the consumer is told
+    }
+}
+
+__global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
+    tail_kernel(GmcDev d, double* bed_all, double* mcres_all, double* ssq_all, const uint64_t* __restrict__ seeds, uint64_t iter0,
+                int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache, int64_t cache_stride,
+                int64_t cache_offset, int32_t* resampled_all, int resync_every, int tile_off, const double* ring, int64_t fstride,
+                int depth, int* flags, int* err, unsigned spin_limit) {
+    __shared__ double scratch[40];
+    __shared__ StepScalars sc, sc_next;
+    __shared__ GmcPair s_pair;
+    __shared__ StepTables s_tab;
+    __shared__ __align__(8) uint64_t tile_bar;
+    double* buf = reinterpret_cast<double*>(gmc_smem);
+    const int64_t plane = (int64_t)d.H * d.W;
+    const int c = blockIdx.x;
+    PhaseClock pc;
+    pc.acc = nullptr;
+    if (threadIdx.x == 0) mbar_init(&tile_bar, 1);
+    const bool vec = (d.W % 2 == 0) && ((reinterpret_cast<uintptr_t>(bed_all) & 15) == 0);
+    double* bed = bed_all + c * plane;
+    double* mcres = mcres_all + c * plane;
+    int32_t* resampled = resampled_all ? resampled_all + c * plane : nullptr;
+    const Philox rng(seeds[c]);
+    double ssq = __ldcg(ssq_all + c);
+    if (threadIdx.x < 32) prepare_step(d, rng, iter0, sc_next, s_pair, s_tab, vec);
+    __syncthreads();
+    if (threadIdx.x == 0) sc = sc_next;
+    __syncthreads();
+    int64_t to_resync = -1;
+    if (resync_every > 0) to_resync = (int64_t)((uint64_t)resync_every - iter0 % (uint64_t)resync_every) % resync_every;
+    const FieldView fv = {};
+    for (int k = 0; k < n_steps; ++k) {
+        const uint64_t it = iter0 + (uint64_t)k;
+        const uint32_t it_lo = (uint32_t)it, it_hi = (uint32_t)(it >> 32);
+        if (to_resync == 0) {
+            ssq = resync_ssq(d, mcres, scratch);
+            to_resync = resync_every;
+        }
+        --to_resync;
+        stage_block_async(sc, d.H, d.W, bed, mcres, buf + tile_off, vec, vec ? &tile_bar : nullptr);
+        if (threadIdx.x == 0) split_wait(flags + 2 * c, k + 1, err, spin_limit);      // the producer has published field k
+        __syncthreads();
+        const double* f = ring + ((int64_t)c * depth + (k % depth)) * fstride;
+        const NextStep next = {&sc_next, &s_pair, &s_tab, it + 1, vec};
+        step_tail<true, true>(d, &sc, scratch, fv, f, sc.w, rng, it_lo, it_hi, buf + tile_off, buf, bed, mcres, ssq, resampled,
+                              nullptr, pc, &next, vec ? &tile_bar : nullptr, (unsigned)k & 1u, err, flags + 2 * c + 1, k + 1);
+        if (threadIdx.x == 0) {
+            const int64_t slot = (int64_t)c * cache_stride + cache_offset + k;
+            if (loss_cache) loss_cache[slot] = div_rn(ssq, d.two_sigma2);
+            if (step_cache) step_cache[slot] = (uint8_t)sc.accept;
+            if (blocks_cache) reinterpret_cast<int4*>(blocks_cache)[slot] = make_int4(sc.ix, sc.iy, sc.h, sc.w);
+            sc = sc_next;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) __stcg(ssq_all + c, ssq);
+}
+
 __global__ void __launch_bounds__(GMC_STEP_THREADS)
     step_injected_kernel(GmcDev d, double* bed_all, double* mcres_all, double* ssq_all, const double* __restrict__ f_all,
                          int64_t f_stride, const int32_t* __restrict__ hw, const int32_t* __restrict__ centre,
