@@ -259,12 +259,13 @@ GMC_API int64_t gmc_launch_count(const gmc_ctx* ctx);
 /* Dynamic shared memory (bytes) and threads per CTA of the fused step kernel for the current block table. */
 GMC_API int gmc_step_kernel_info(const gmc_ctx* ctx, int* smem_bytes, int* threads, int* ctas_per_sm);
 
-/* Launch shape policy of gmc_run's step kernels: 0 = auto (a launch with at most half as many chains as the GPU has CTA
- * slots runs in SPLIT mode - per chain a producer CTA that synthesises the proposal fields of the coming steps and a
- * consumer CTA that runs the Metropolis tail, pipelined across steps; otherwise one fused 256-thread CTA per chain, two per
- * SM), 1 = always the fused 256-thread kernel (for launches that share the GPU with other launches: chain ranges on several
- * streams, several steps in flight), 2 = fused 512-thread CTAs (one per SM) whenever the launch is not chunk-scheduled,
- * 3 = split whenever it fits.  Trajectories do not depend on the choice (bit-identical). */
+/* Launch shape policy of gmc_run's step kernels: 0 = auto (a launch with no more chains than the GPU has SMs gets 512-thread
+ * CTAs, one per SM, so a chain uses all the warps of its SM; otherwise 256-thread CTAs, two per SM), 1 = always 256 threads
+ * (for launches that share the GPU with other launches: chain ranges on several streams, several steps in flight),
+ * 2 = 512 threads whenever the launch is not chunk-scheduled, 3 = SPLIT when fewer than half as many chains as CTA slots
+ * (experimental: per chain a producer CTA that synthesises the proposal fields of the coming steps and a consumer CTA that
+ * runs the Metropolis tail, pipelined across steps; measured slower than mode 2).  Trajectories do not depend
+ * on the choice (bit-identical). */
 GMC_API int gmc_set_step_cta(gmc_ctx* ctx, int mode);
 
 /* Reports - then clears - the device-error flag (synchronize != 0: after waiting for the device; 0: as stored by the

@@ -327,9 +327,9 @@ class Context:
             sms = torch.cuda.get_device_properties(self.device).multi_processor_count
             slots = c.value * sms
             mode = getattr(self, "_cta_mode", 0)
-            split = (mode in (0, 3)) and 2 * n_chains <= slots
+            split = mode == 3 and 2 * n_chains < slots
             if os.environ.get("GMC_STEP_SPLIT") is not None:
-                split = os.environ["GMC_STEP_SPLIT"][:1] == "1" and 2 * n_chains <= slots
+                split = os.environ["GMC_STEP_SPLIT"][:1] == "1" and 2 * n_chains < slots
             wide = (not split) and ((mode == 0 and n_chains <= sms) or mode == 2)
             if os.environ.get("GMC_STEP_WIDE") is not None:
                 wide = (not split) and os.environ["GMC_STEP_WIDE"][:1] == "1" and n_chains <= slots

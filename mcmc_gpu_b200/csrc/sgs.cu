@@ -874,6 +874,7 @@ __global__ void __launch_bounds__(SGS_THREADS)
                     const int jj = (int)(it2 / C);
                     unsigned spins = 0;
                     while (*done < jj) {
+                        if (*(volatile int*)dev_err) break;   // a wait already gave up: the launch is void, do not wait again
                         __nanosleep(200);
                         if (++spins > spin_limit) {           // an item only waits for items drawn earlier; never hang, and
                             *(volatile int*)dev_err = GMC_DEVERR_WAIT_TIMEOUT;   // never carry on silently (host: GMC_ECUDA)

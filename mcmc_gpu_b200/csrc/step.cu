@@ -209,15 +209,18 @@ extern "C" int gmc_run(gmc_ctx* c, double* bed, double* mcres, double* ssq, cons
         chunk = std::min(256, std::max(4, (n_steps + 31) / 32));
     }
     // Launches that under-fill the GPU (auto mode; gmc_set_step_cta(1) = "this launch shares the GPU" disables both):
-    //  * at most half as many chains as CTA slots: SPLIT mode - a producer CTA synthesises the fields of the coming steps
-    //    while the consumer CTA of the same chain runs the Metropolis tail (two kernels, the producer on the context's
-    //    auxiliary stream, fenced to the caller's stream by events);
-    //  * else no more chains than SMs: 512-thread CTAs, one per SM.
+    //  * no more chains than SMs: 512-thread CTAs, one per SM;
+    //  * opt-in, fewer than half as many chains as CTA slots: SPLIT mode - a producer CTA synthesises the fields of the
+    //    coming steps while the consumer CTA of the same chain runs the Metropolis tail (two kernels, the producer on the
+    //    context's auxiliary stream, fenced to the caller's stream by events).
     static const char* wide_env = getenv("GMC_STEP_WIDE");            // "0" / "1" force the 512-thread choice (A/B runs)
     static const char* split_env = getenv("GMC_STEP_SPLIT");          // "0" / "1" force the split choice (A/B runs)
-    bool split = !sched && c->step_cta_mode == 0 && 2 * C <= slots && n_steps >= 4;
-    if (c->step_cta_mode == 3) split = !sched && 2 * C <= slots;
-    if (split_env) split = !sched && 2 * C <= slots && split_env[0] == '1';
+    // (split is opt-in - mode 3 / GMC_STEP_SPLIT=1: measured 3.57 M chain-steps/s for 128 x 500^2 and 2.79 M for 128 x 2000^2
+    // against 4.86 M / 4.36 M with 512-thread CTAs: the producer's per-step scalar preparation, hidden behind the residual
+    // phase by the helper warp in the fused kernel, is exposed there)
+    bool split = false;
+    if (c->step_cta_mode == 3) split = !sched && 2 * C < slots;
+    if (split_env) split = !sched && 2 * C < slots && split_env[0] == '1';
     bool wide = !split && !sched && c->step_wide_ctas >= 1 && C <= c->sm_count;
     if (c->step_cta_mode == 1 || c->step_cta_mode == 3) wide = false;  // gmc_set_step_cta: the launch shares the GPU / split only
     if (c->step_cta_mode == 2) wide = !sched && c->step_wide_ctas >= 1;

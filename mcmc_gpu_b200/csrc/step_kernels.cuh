@@ -1049,6 +1049,7 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
                     volatile int* done = sched + 1 + cc;
                     unsigned spins = 0;
                     while (*done < jj) {
+                        if (*(volatile int*)err) break;       // a wait already gave up: the launch is void, do not wait again
                         __nanosleep(200);
                         if (++spins > spin_limit) {           // never hang the device - and never carry on silently: the
                             *(volatile int*)err = GMC_DEVERR_WAIT_TIMEOUT;   // host turns the flag into GMC_ECUDA
@@ -1130,6 +1131,7 @@ __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
 __device__ __forceinline__ void split_wait(volatile int* flag, int need, int* err, unsigned spin_limit) {
     unsigned spins = 0;
     while (*flag < need) {
+        if (*(volatile int*)err) break;                       // a wait already gave up: the launch is void, do not wait again
         __nanosleep(100);
         if (++spins > spin_limit) {
             *(volatile int*)err = GMC_DEVERR_WAIT_TIMEOUT;
