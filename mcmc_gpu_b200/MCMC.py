@@ -914,7 +914,7 @@ class ChainBatch:
 
     def advance(self, n_steps, resync_every=4096, want_caches=True):
         """n_steps fused free-running iterations (kernel K1+K4).  Returns (loss[C,n], accepted[C,n], blocks[C,n,4])."""
-        self.ctx.set_step_cta("auto")
+        self.ctx.set_step_cta(getattr(self, "step_cta", "auto"))     # "auto" | "narrow" | "wide" | "split" (gmc_set_step_cta)
         lc = st = bl = None
         if want_caches:
             lc, st, bl = self._device_caches(n_steps)
@@ -932,7 +932,7 @@ class ChainBatch:
         as stacked arrays; results land in the pinned tensors of `out` when given (one D2H copy each)."""
         torch = self.torch
         n = n_steps + 1
-        self.ctx.set_step_cta("auto")
+        self.ctx.set_step_cta(getattr(self, "step_cta", "auto"))
         lc, st, bl = self._device_caches(n)
         lc[:, 0] = self._loss_now()
         st[:, 0] = 0

@@ -161,6 +161,14 @@ def test_free_run_at_500_matches_the_emulated_oracle():
     wide = MCMC.ChainBatch(ch, rf, np.stack([g["bed0"]] * 150), [key] + [MCMC.philox_key(s) for s in range(149)], iter0=1)
     _, st2, bl2 = wide.advance(n_steps, resync_every=0)
     assert np.array_equal(st2[0], st[0]) and np.array_equal(bl2[0], bl[0]) and bits_equal(wide.beds()[0], batch.beds()[0])
+    # ... and in split mode (a field-producer CTA and a Metropolis-tail CTA per chain, pipelined across steps): bit-identical
+    split = MCMC.ChainBatch(ch, rf, np.stack([g["bed0"]] * 3), [key, MCMC.philox_key(7), MCMC.philox_key(8)], iter0=1,
+                            track_resampled=True)
+    split.step_cta = "split"
+    _, st3, bl3 = split.advance(n_steps, resync_every=0)
+    assert split.ctx.step_kernel_info(3).get("ctas_per_chain") == 2
+    assert np.array_equal(st3[0], st[0]) and np.array_equal(bl3[0], bl[0]) and bits_equal(split.beds()[0], batch.beds()[0])
+    assert np.array_equal(split.resampled_times()[0], batch.resampled_times()[0])
 
 
 def test_2000_grid_real_weight_and_replayed_oracle_steps():
