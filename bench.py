@@ -296,16 +296,20 @@ def build_chain(MCMC, syn, H, W, quiet):
 
 def device_initial_beds(torch, bed0, chain0, C, dev, amplitude=5.0):
     """[C,H,W] initial beds on the device: bed0 plus a smooth bump whose phases depend on the GLOBAL chain id (the same
-    recipe as synthetic.chain_initial_beds, evaluated by torch so 4096 x 500^2 beds need no 8 GB host array)."""
+    recipe as synthetic.chain_initial_beds, evaluated by torch in chunks of 128 chains so 4096 x 500^2 beds need no 8 GB
+    host array and only a handful of kernel launches)."""
     H, W = bed0.shape
-    ii = torch.arange(H, dtype=torch.float64, device=dev)[:, None]
-    jj = torch.arange(W, dtype=torch.float64, device=dev)[None, :]
+    ii = torch.arange(H, dtype=torch.float64, device=dev)[None, :, None] / 37.0
+    jj = torch.arange(W, dtype=torch.float64, device=dev)[None, None, :] / 41.0
     b0 = torch.as_tensor(bed0).to(dev)
     out = torch.empty((C, H, W), dtype=torch.float64, device=dev)
-    for c in range(C):
-        ph = np.random.default_rng(10_000 + chain0 + c).uniform(0.0, 2.0 * np.pi, size=2)
-        amp = 0.0 if chain0 + c == 0 else amplitude
-        out[c] = b0 + amp * torch.sin(ii / 37.0 + ph[0]) * torch.cos(jj / 41.0 + ph[1])
+    ph = np.stack([np.random.default_rng(10_000 + chain0 + c).uniform(0.0, 2.0 * np.pi, size=2) for c in range(C)]) if C else np.zeros((0, 2))
+    amp = np.where(np.arange(C) + chain0 == 0, 0.0, amplitude)
+    for lo in range(0, C, 128):
+        hi = min(C, lo + 128)
+        p = torch.as_tensor(ph[lo:hi]).to(dev)
+        a = torch.as_tensor(amp[lo:hi]).to(dev)[:, None, None]
+        out[lo:hi] = b0[None] + a * torch.sin(ii + p[:, 0, None, None]) * torch.cos(jj + p[:, 1, None, None])
     return out
 
 
