@@ -1152,7 +1152,7 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
 //   1. sgs_grid_solve_kernel: all nodes of all realisations in parallel, one warp per node: octant search in the ORDER
 //      grid (ord[cell] = -1 for conditioning data, else the cell's position in the path; a cell is available to node t
 //      iff ord < t), kriging solve (sgs_warp_solve), record (neighbour cells, weights, sd) to global memory;
-//   2. sgs_grid_values_kernel: one warp per realisation walks its path: value = est + sd * noise with
+//   2. sgs_grid_values_kernel: sixteen warps per realisation walk its path (see the kernel): value = est + sd * noise with
 //      est = mean + sum w_i (v_i - mean) over the recorded neighbours (a sparse triangular solve), the truncated-normal
 //      draw when bounds are given (interpolate.py:166-181), writing the normal-score grid in place.
 // =====================================================================================================================
@@ -1267,31 +1267,75 @@ __device__ __forceinline__ double truncnorm_ppf(double u, double a, double b) {
     return normcdfinv(pa + u * (pb - pa));
 }
 
-__global__ void __launch_bounds__(32)
+// One CTA of SGV_WARPS warps per realisation; warp w takes the path nodes w, w + SGV_WARPS, ... in order.  A node's value
+// needs the values of its recorded neighbours, all EARLIER in the path: cells still to be simulated hold NaN in z, so a
+// lane simply re-reads its neighbour (through L2) until it is a number.  The warp working on the earliest unfinished node
+// never waits, so the walk cannot deadlock; neighbours are rarely among the last SGV_WARPS path positions, so the warps
+// mostly run independently and the dependent chain of the one-warp-per-realisation walk (2.2 us per node: record, gather,
+// reduce, store) is overlapped SGV_WARPS-fold.  Same arithmetic in the same order per node: results are bit-identical to
+// the sequential walk.  (A neighbour that is genuinely NaN - a NaN weight or bound upstream - stops the waiting after a
+// bound and propagates, as it would sequentially.)
+#define SGV_WARPS 16
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(SGV_WARPS * 32)
     sgs_grid_values_kernel(int H, int W, double* __restrict__ z_all, const int32_t* __restrict__ path_all, int64_t n_path,
                            const int32_t* __restrict__ rec_n, const int32_t* __restrict__ rec_idx,
                            const double* __restrict__ rec_w, const double* __restrict__ rec_sd,
                            const double* __restrict__ noise_all, const double* __restrict__ blo, const double* __restrict__ bhi) {
-    const int r = blockIdx.x, lane = threadIdx.x;
+    __shared__ int poisoned;                                 // some warp met a neighbour that never became a number
+    const int r = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int64_t plane = (int64_t)H * W;
     double* z = z_all + r * plane;
     const int32_t* path = path_all + r * n_path;
     const int64_t base = (int64_t)r * n_path;
-    for (int64_t t = 0; t < n_path; ++t) {
+    if (threadIdx.x == 0) poisoned = 0;
+    __syncthreads();
+    for (int64_t t = wid; t < n_path; t += SGV_WARPS) {
         const int n = rec_n[base + t];
-        if (n < 0) continue;
+        if (n < 0) continue;                                 // conditioning cell (warp-uniform)
         const int cell = path[t];
+        int idx[2] = {0, 0};
+        double w[2] = {0.0, 0.0}, v[2] = {0.0, 0.0};
+        bool need[2];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            const int q = lane + 32 * h2;
+            need[h2] = q < n;
+            if (need[h2]) {
+                idx[h2] = __ldg(rec_idx + (base + t) * SGS_WN + q);
+                w[h2] = __ldg(rec_w + (base + t) * SGS_WN + q);
+            }
+        }
+        const double sd = rec_sd[base + t], nz = noise_all[base + t];      // independent of the values: in flight early
+        unsigned spins = 0;
+        for (;;) {
+            bool pending = false;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2)
+                if (need[h2]) {
+                    v[h2] = ld_cg_f64(z + idx[h2]);
+                    if (v[h2] == v[h2]) need[h2] = false;
+                    else pending = true;
+                }
+            if (!__any_sync(0xffffffffu, pending)) break;
+            if (*(volatile int*)&poisoned || ++spins > (1u << 18)) {      // never hang: carry the NaN like the sequential walk
+                poisoned = 1;
+                break;
+            }
+        }
         double sv = 0.0, swv = 0.0, sw = 0.0;
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
             const int q = lane + 32 * h2;
             if (q < n) {
-                const int idx = __ldg(rec_idx + (base + t) * SGS_WN + q);
-                const double w = __ldg(rec_w + (base + t) * SGS_WN + q);
-                const double v = __ldcg(z + idx);
-                sv += v;
-                swv += w * v;
-                sw += w;
+                sv += v[h2];
+                swv += w[h2] * v[h2];
+                sw += w[h2];
             }
         }
 #pragma unroll
@@ -1305,7 +1349,6 @@ __global__ void __launch_bounds__(32)
             if (n > 0) {
                 const double mean = sv / (double)n;
                 const double est = mean + (swv - mean * sw);             // = mean + sum w (v - mean)     _krige.py:42
-                const double sd = rec_sd[base + t], nz = noise_all[base + t];
                 if (!blo) val = est + sd * nz;                           // rng.normal(est, sd)           :173
                 else {
                     const double lo = blo[cell], hi = bhi[cell];
@@ -1314,8 +1357,8 @@ __global__ void __launch_bounds__(32)
                 }
             }
             __stcg(z + cell, val);
+            __threadfence();                                 // visible to the warps (of this CTA, on this SM or through L2) that wait for it
         }
-        __threadfence_block();
         __syncwarp();
     }
 }
@@ -1370,6 +1413,17 @@ extern "C" int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, 
     return GMC_OK;
 }
 
+// cells to simulate get the "not yet simulated" marker (NaN) whatever the caller left there
+__global__ void sgs_grid_mark_kernel(int H, int W, double* __restrict__ z_all, const int32_t* __restrict__ path_all, int64_t n_path,
+                                     const int32_t* __restrict__ rec_n, int64_t total) {
+    const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= total) return;
+    if (rec_n[item] >= 0) {
+        const int64_t r = item / n_path;
+        z_all[r * (int64_t)H * W + path_all[item]] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
 extern "C" int gmc_sgs_grid_values(int device, int H, int W, double* z, const int32_t* path, int64_t n_path, int n_real,
                                    const int32_t* rec_n, const int32_t* rec_idx, const double* rec_w, const double* rec_sd,
                                    const double* noise, const double* bound_lo, const double* bound_hi, void* stream) {
@@ -1377,7 +1431,9 @@ extern "C" int gmc_sgs_grid_values(int device, int H, int W, double* z, const in
     if ((bound_lo == nullptr) != (bound_hi == nullptr)) GMC_FAIL(GMC_EINVAL, "gmc_sgs_grid_values: give both bounds or neither");
     if (H < 1 || W < 1 || n_path < 1 || n_real < 1) GMC_FAIL(GMC_ESHAPE, "gmc_sgs_grid_values: bad sizes");
     GMC_CUDA(cudaSetDevice(device));
-    sgs_grid_values_kernel<<<n_real, 32, 0, (cudaStream_t)stream>>>(H, W, z, path, n_path, rec_n, rec_idx, rec_w, rec_sd, noise,
+    const int64_t total = (int64_t)n_real * n_path;
+    sgs_grid_mark_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(H, W, z, path, n_path, rec_n, total);
+    sgs_grid_values_kernel<<<n_real, SGV_WARPS * 32, 0, (cudaStream_t)stream>>>(H, W, z, path, n_path, rec_n, rec_idx, rec_w, rec_sd, noise,
                                                                     bound_lo, bound_hi);
     GMC_CUDA(cudaGetLastError());
     return GMC_OK;
