@@ -223,7 +223,7 @@ GMC_API int gmc_sgs_grid_solve(int device, int H, int W, const int32_t* ord, con
                        void* stream);
 
 /* The draws in path order (interpolate.py:166-183): z dev [n_real][H*W] holds the normal-scored data (anything elsewhere: the cells to simulate are
- * first marked NaN, the readiness marker of the dependency-driven walk - sixteen warps per realisation)
+ * first marked NaN, the readiness marker of the dependency-driven walk - thirty-two warps per realisation)
  * and receives the simulated normal scores; noise dev [n_real][n_path]: the standard normal of node t (no bounds) or
  * the uniform of its truncated-normal draw; bound_lo / bound_hi dev [H*W] normal-scored bounds, or both NULL. */
 GMC_API int gmc_sgs_grid_values(int device, int H, int W, double* z, const int32_t* path, int64_t n_path, int n_real,

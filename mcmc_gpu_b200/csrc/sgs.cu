@@ -1152,7 +1152,7 @@ extern "C" int gmc_sgs_run(gmc_ctx* c, double* bedc, double* z, double* mcres, d
 //   1. sgs_grid_solve_kernel: all nodes of all realisations in parallel, one warp per node: octant search in the ORDER
 //      grid (ord[cell] = -1 for conditioning data, else the cell's position in the path; a cell is available to node t
 //      iff ord < t), kriging solve (sgs_warp_solve), record (neighbour cells, weights, sd) to global memory;
-//   2. sgs_grid_values_kernel: sixteen warps per realisation walk its path (see the kernel): value = est + sd * noise with
+//   2. sgs_grid_values_kernel: thirty-two warps per realisation walk its path (see the kernel): value = est + sd * noise with
 //      est = mean + sum w_i (v_i - mean) over the recorded neighbours (a sparse triangular solve), the truncated-normal
 //      draw when bounds are given (interpolate.py:166-181), writing the normal-score grid in place.
 // =====================================================================================================================
@@ -1275,7 +1275,7 @@ __device__ __forceinline__ double truncnorm_ppf(double u, double a, double b) {
 // reduce, store) is overlapped SGV_WARPS-fold.  Same arithmetic in the same order per node: results are bit-identical to
 // the sequential walk.  (A neighbour that is genuinely NaN - a NaN weight or bound upstream - stops the waiting after a
 // bound and propagates, as it would sequentially.)
-#define SGV_WARPS 16
+#define SGV_WARPS 32
 __device__ __forceinline__ double ld_cg_f64(const double* p) {
     double v;
     asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
