@@ -436,48 +436,65 @@ __device__ void sgs_one_step(const GmcDev& d, const SgsDev& s, SgsShared& S, dou
         __syncthreads();
         const int n_todo = S.n_todo;
         SgsWarpRec* recs = reinterpret_cast<SgsWarpRec*>(S.sig);
-        for (int t0 = 0; t0 < n_todo; t0 += 8) {
-            // ... phase 1: eight path nodes, one per warp (search + solve; no simulated value is read)
-            if (t0 + wid < n_todo) sgs_warp_node<INJECT>(d, s, S, recs[wid], z, t0 + wid, bw, zn_in, rng, it_lo, it_hi);
-            __syncthreads();
-            mark(4);
-            // ... phase 2: values in path order                                                    MCMC.py:163-169
-            if (wid == 0) {
-                const int nb = min(8, n_todo - t0);
-                for (int q = 0; q < nb; ++q) {
-                    const SgsWarpRec& R = recs[q];
-                    const int n = R.n;
-                    double val = 0.0;
-                    if (n == 0) {
-                        if (lane == 0) S.err = 1;
-                    } else {
-                        double v[2] = {0.0, 0.0}, wv[2] = {0.0, 0.0};
+        // ... every warp walks its own nodes t = wid, wid + 8, ... of the path: search + solve (no simulated value is read),
+        // then the value, for which the in-block neighbours - all EARLIER in the path - must have been simulated: a cell
+        // still to be simulated holds NaN in S.blk_z, so a lane re-reads its neighbour until it is a number.  The warp on
+        // the earliest unfinished node never waits (no deadlock), and there is no CTA barrier and no serial values pass
+        // between batches of eight nodes any more (they cost 28 % of the node time: profiles/README.md).
+        volatile double* blk = S.blk_z;
+        for (int t = wid; t < n_todo; t += 8) {
+            SgsWarpRec& R = recs[wid];
+            sgs_warp_node<INJECT>(d, s, S, R, z, t, bw, zn_in, rng, it_lo, it_hi);
+            const int n = R.n;
+            double val = 0.0;
+            if (n == 0) {
+                if (lane == 0) S.err = 1;
+            } else {
+                double v[2] = {0.0, 0.0}, wv[2] = {0.0, 0.0};
+                int src[2] = {-1, -1};
+                bool need[2] = {false, false};
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            const int r = lane + 32 * h2;
-                            if (r < n) {
-                                const int src = R.nsrc[r];
-                                v[h2] = (src >= 0) ? S.blk_z[src] : R.nval[r];
-                                wv[h2] = R.w[r];
-                            }
-                        }
-                        double sv = warp_sum(v[0] + v[1]);
-                        sv = __shfl_sync(0xffffffffu, sv, 0);
-                        const double mean = sv / (double)n;
-                        double pe = 0.0;
-#pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2)
-                            if (lane + 32 * h2 < n) pe += wv[h2] * (v[h2] - mean);
-                        pe = warp_sum(pe);
-                        val = (mean + pe) + sqrt(R.var) * R.zn;                          // MCMC.py:168
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int r = lane + 32 * h2;
+                    if (r < n) {
+                        src[h2] = R.nsrc[r];
+                        wv[h2] = R.w[r];
+                        if (src[h2] >= 0) need[h2] = true;
+                        else v[h2] = R.nval[r];
                     }
-                    if (lane == 0) S.blk_z[R.node] = val;
-                    __syncwarp();
                 }
+                unsigned spins = 0;
+                for (;;) {                                    // MCMC.py:163-169: values in path order
+                    bool pending = false;
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2)
+                        if (need[h2]) {
+                            v[h2] = blk[src[h2]];
+                            if (v[h2] == v[h2]) need[h2] = false;
+                            else pending = true;
+                        }
+                    if (!__any_sync(0xffffffffu, pending)) break;
+                    if (++spins > (1u << 22)) break;          // a genuinely NaN neighbour: carry it, never hang
+                }
+                double sv = warp_sum(v[0] + v[1]);
+                sv = __shfl_sync(0xffffffffu, sv, 0);
+                const double mean = sv / (double)n;
+                double pe = 0.0;
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2)
+                    if (lane + 32 * h2 < n) pe += wv[h2] * (v[h2] - mean);
+                pe = warp_sum(pe);
+                val = (mean + pe) + sqrt(R.var) * R.zn;                                  // MCMC.py:168
             }
-            __syncthreads();
-            mark(5);
+            if (lane == 0) {
+                blk[R.node] = val;
+                __threadfence_block();
+            }
+            __syncwarp();
         }
+        __syncthreads();
+        mark(4);
+        mark(5);
     } else {
     // (2) sequential simulation along the path                                              MCMC.py:130-169
     for (int k = 0; k < nblk; ++k) {
