@@ -490,8 +490,10 @@ static bool launch_tma_variant(gmc_ctx* c, cudaStream_t st, const double* bed, d
     // again (measured: 4096 chains in 7 groups 72 % of the HBM peak vs 82 % for 256 chains in 7 groups)
     const int g_min = std::max(1, (C + 47) / 48);
     for (int G = g_min; G <= std::max(g_min, std::min(C / 4, 4096)); ++G) {
+        // cost model fitted to the sweeps in profiles/r2/stencil_groups.txt: a CTA's prologue costs about one chain-iteration,
+        // and the tail of the grid about one CTA duration (CTAs differ: boundary tiles, the producer warp), i.e. 1 / waves
         const double n = (double)C / G, waves = (double)tx * ty * G / slots;
-        const double score = n / (n + 3.0) * (waves / std::ceil(waves)) * (waves < 1.0 ? waves : 1.0);
+        const double score = n / (n + 1.0) * waves / (waves + 1.0);
         if (score > best + 1e-9) {
             best = score;
             groups = G;

@@ -167,8 +167,9 @@ __device__ __forceinline__ void r2_rows(const R2Lane& L, const GmcDev& d, unsign
         num[k][3] = sub_rn(fy1[k + 2], fy1[k]);
         const double rd[4] = {rdx0, rdx1, rdy, rdy}, dn[4] = {dnx0, dnx1, dny, dny};
         if (!EXACT) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) quo[k][j] = num[k][j] * rd[j];
+            if (EDGE) {                                            // per-cell divisors: two fmas per cell, see below
+                quo[k][0] = rdx0; quo[k][1] = rdx1; quo[k][2] = quo[k][3] = rdy;
+            }
             continue;
         }
 #pragma unroll
@@ -202,9 +203,9 @@ __device__ __forceinline__ void r2_rows(const R2Lane& L, const GmcDev& d, unsign
         if (EXACT) {
             r[k].x = sub_rn(add_rn(add_rn(quo[k][0], quo[k][2]), L.dh[k].x), L.sm[k].x);
             r[k].y = sub_rn(add_rn(add_rn(quo[k][1], quo[k][3]), L.dh[k].y), L.sm[k].y);
-        } else if (EDGE) {                                         // L.dh holds dhdt - smb
-            r[k].x = (quo[k][0] + quo[k][2]) + L.dh[k].x;
-            r[k].y = (quo[k][1] + quo[k][3]) + L.dh[k].y;
+        } else if (EDGE) {                                         // L.dh holds dhdt - smb; quo holds the reciprocals
+            r[k].x = fma(num[k][0], quo[k][0], fma(num[k][2], quo[k][2], L.dh[k].x));
+            r[k].y = fma(num[k][1], quo[k][1], fma(num[k][3], quo[k][3], L.dh[k].y));
         } else {                                                   // one divisor: (numx + numy) / (2 res) + (dhdt - smb)
             r[k].x = fma(num[k][0] + num[k][2], r_two_res, L.dh[k].x);
             r[k].y = fma(num[k][1] + num[k][3], r_two_res, L.dh[k].y);
