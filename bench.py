@@ -495,7 +495,7 @@ def gpu_main(a):
     host_beds.copy_(device_initial_beds(torch, g["bed0"], chain0, C, dev).cpu())
     outs = [{"bed": pinned((C, H, W), torch.float64), "loss": pinned((C, n_it + 1), torch.float64),
              "steps": pinned((C, n_it + 1), torch.uint8), "blocks": pinned((C, n_it + 1, 4), torch.int32),
-             "resampled": pinned((C, H, W), torch.int32)} for _ in range(NBUF)]
+             "resampled": pinned((C, H, W), torch.int16)} for _ in range(NBUF)]     # counts <= 1000 proposals: int16 on the link
     keys = [MCMC.philox_key(s, s) for s in seeds]
     batches = [MCMC.ChainBatch(ch, rf, host_beds, keys, device=dev, track_resampled=True) for _ in range(NBUF)]
     batch = batches[0]

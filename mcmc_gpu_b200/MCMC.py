@@ -882,7 +882,7 @@ class ChainBatch:
         self.ctx.residual_loss(self.bed, self.mcres, self._loss, self.ssq)
 
     def close(self):
-        self.bed = self.mcres = self.resampled = self._cache = None
+        self.bed = self.mcres = self.resampled = self._cache = self._counts16 = None
 
     def _loss_now(self):
         # tensor / tensor is an IEEE division on the device (tensor / python scalar multiplies by a reciprocal)
@@ -903,6 +903,23 @@ class ChainBatch:
         if self.resampled is None:
             raise GmcError("ChainBatch was created with track_resampled=False")
         return self.resampled.cpu().numpy().astype(np.float64) * self.gate[None].astype(np.float64)
+
+    def _copy_counts(self, dst, a, b, n_steps):
+        """Coverage counts of chains [a, b) -> the pinned tensor `dst` (queued on the current stream).  `dst` may be int32
+        (the device dtype) or int16: a count cannot exceed the number of proposals, so for runs of up to 32767 proposals the
+        narrower type halves the largest download after the beds (the host link is what bounds the end-to-end rate on 8 GPUs)."""
+        torch = self.torch
+        if dst.dtype == self.resampled.dtype:
+            dst[a:b].copy_(self.resampled[a:b], non_blocking=True)
+            return
+        if dst.dtype != torch.int16:
+            raise ValueError("out['resampled'] must be an int32 or int16 tensor")
+        if n_steps > 32767:
+            raise ValueError("int16 coverage counts need at most 32767 proposals per run; pass an int32 tensor")
+        if getattr(self, "_counts16", None) is None:
+            self._counts16 = torch.empty((self.C, self.H, self.W), dtype=torch.int16, device=self.dev)
+        self._counts16[a:b].copy_(self.resampled[a:b])                      # narrowing on the device
+        dst[a:b].copy_(self._counts16[a:b], non_blocking=True)
 
     def _device_caches(self, n):
         torch = self.torch
@@ -946,7 +963,7 @@ class ChainBatch:
             out["steps"].copy_(st, non_blocking=True)
             out["blocks"].copy_(bl, non_blocking=True)
             if "resampled" in out and self.resampled is not None:
-                out["resampled"].copy_(self.resampled, non_blocking=True)
+                self._copy_counts(out["resampled"], 0, self.C, n_steps)
             torch.cuda.current_stream().synchronize()
             self.ctx.check_flag()
             return dict(out)
@@ -1024,7 +1041,7 @@ class ChainBatch:
                 out["steps"][a:b].copy_(st[a:b], non_blocking=True)
                 out["blocks"][a:b].copy_(bl[a:b], non_blocking=True)
                 if "resampled" in out:
-                    out["resampled"][a:b].copy_(self.resampled[a:b], non_blocking=True)
+                    self._copy_counts(out["resampled"], a, b, n_steps)
                 mark(g, 3)
         self.iteration = int(iter0) + n_steps
         pending = PendingRun(self, out)

@@ -169,6 +169,27 @@ def test_pipelined_run_many_equals_plain_run_many():
     assert bits_equal(res["bed"].numpy(), plain["bed"])
     assert np.array_equal(res["steps"].numpy(), plain["steps"]) and np.array_equal(res["blocks"].numpy()[:, 1:], plain["blocks"][:, 1:].astype(np.int32))
     assert np.allclose(res["loss"].numpy(), plain["loss"], rtol=1e-13, atol=0)
+    # round 2: full output contract (coverage counts, int32 or int16 on the link), two steps in flight on two batches
+    # (wait=False handles), and the reference's list of 7-tuples from the pipelined path without running twice
+    ref_b = MCMC.ChainBatch(ch, rf, beds0, [MCMC.philox_key(s, s) for s in seeds], track_resampled=True)
+    ref_b.advance(n_iter - 1)
+    counts = ref_b.resampled.cpu().numpy()
+    batches = [MCMC.ChainBatch(ch, rf, host, [MCMC.philox_key(s, s) for s in seeds], track_resampled=True) for _ in range(2)]
+    outs = []
+    for dt in (torch.int32, torch.int16):
+        o = {k: torch.empty_like(v).pin_memory() for k, v in out.items()}
+        o["resampled"] = torch.empty((C,) + g["bed0"].shape, dtype=dt).pin_memory()
+        outs.append(o)
+    pend = [quiet(ch.run_many, n_iter, rf, host, seeds, as_arrays=True, batch=batches[k], out=outs[k], wait=False) for k in range(2)]
+    for k in range(2):
+        r = pend[k].wait()
+        assert bits_equal(r["bed"].numpy(), plain["bed"]) and np.array_equal(r["steps"].numpy(), plain["steps"])
+        assert np.array_equal(r["resampled"].numpy().astype(np.int32), counts)
+    tuples = quiet(ch.run_many, n_iter, rf, host, seeds, batch=batches[0], out=outs[0])
+    assert len(tuples) == C and bits_equal(tuples[2][0], plain["bed"][2]) and np.isnan(tuples[2][6][0]).all()
+    assert np.array_equal(tuples[2][5], ref_b.resampled_times()[2]) and batches[0].bed is not None      # caller's batch stays open
+    with pytest.raises(ValueError, match="wait=False"):
+        ch.run_many(n_iter, rf, beds0, seeds, wait=False)
 
 
 def test_more_chains_than_cta_slots_uses_chunked_scheduling_and_stays_bit_identical(monkeypatch):
