@@ -824,7 +824,7 @@ class PendingRun:
         self.batch, self.out = batch, out
         torch = batch.torch
         self._events = []
-        for strm in batch._streams:
+        for strm in batch._pre_streams:                          # the downloads of a range are queued on its high-priority stream
             ev = torch.cuda.Event()
             ev.record(strm)
             self._events.append(ev)
@@ -835,7 +835,7 @@ class PendingRun:
             for ev in self._events:
                 ev.synchronize()
             main = self.batch.torch.cuda.current_stream()
-            for strm in self.batch._streams:
+            for strm in self.batch._pre_streams:
                 main.wait_stream(strm)
             self.batch.ctx.check_flag()
             self._done = True
@@ -1032,10 +1032,12 @@ class ChainBatch:
                 bl[a:b, 0] = -1
                 mark(g, 1)
             strm.wait_stream(pre)
-            with torch.cuda.stream(strm):
+            with torch.cuda.stream(strm):                         # low priority: the step kernel only
                 self.ctx.run(self.bed[a:b], self.mcres[a:b], self.ssq[a:b], self.seeds[a:b], iter0, n_steps, lc[a:b], st[a:b],
                              bl[a:b], 1, None if self.resampled is None else self.resampled[a:b], resync_every)
                 mark(g, 2)
+            pre.wait_stream(strm)
+            with torch.cuda.stream(pre):                          # high priority again: narrowing kernel and the downloads
                 out["bed"][a:b].copy_(self.bed[a:b], non_blocking=True)
                 out["loss"][a:b].copy_(lc[a:b], non_blocking=True)
                 out["steps"][a:b].copy_(st[a:b], non_blocking=True)
