@@ -491,11 +491,17 @@ def gpu_main(a):
 
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype).pin_memory()
+    # Coverage counts travel as int32 (the device type) or int16 (narrowed on the device: -128 MB per step, +one kernel per
+    # chain range that has to squeeze in between the step CTAs).  Measured: one GPU 38.5 ms per step with int32 vs 41.4 ms
+    # with int16 (compute bound: the extra kernel costs more than the bytes save); eight GPUs share one host whose link
+    # bounds the step (profiles/README.md), so there the narrower type is used.
+    counts_bits = int(os.environ.get("GMC_E2E_COUNTS", "16" if world >= 4 else "32"))
+    counts_dtype = torch.int16 if counts_bits == 16 else torch.int32
     host_beds = pinned((C, H, W), torch.float64)
     host_beds.copy_(device_initial_beds(torch, g["bed0"], chain0, C, dev).cpu())
     outs = [{"bed": pinned((C, H, W), torch.float64), "loss": pinned((C, n_it + 1), torch.float64),
              "steps": pinned((C, n_it + 1), torch.uint8), "blocks": pinned((C, n_it + 1, 4), torch.int32),
-             "resampled": pinned((C, H, W), torch.int16)} for _ in range(NBUF)]     # counts <= 1000 proposals: int16 on the link
+             "resampled": pinned((C, H, W), counts_dtype)} for _ in range(NBUF)]
     keys = [MCMC.philox_key(s, s) for s in seeds]
     batches = [MCMC.ChainBatch(ch, rf, host_beds, keys, device=dev, track_resampled=True) for _ in range(NBUF)]
     batch = batches[0]
@@ -658,6 +664,7 @@ def gpu_main(a):
                 "config": cfg, "details": {"acceptance_rate": acc_rate, "step_kernel": info, "cpu_affinity": affinity},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / a.steps, "steps_in_flight": NBUF, "chain_ranges_per_step": E2E_RANGES,
+                        "coverage_counts_dtype": "int%d" % counts_bits,
                         "serial": {"value": total_chains * n_it * a.steps / (e2e_serial_ms * 1e-3), "ms_per_step": e2e_serial_ms / a.steps,
                                    "what": "one step at a time (upload, compute and download of a step finish before the next starts)"},
                         "host_bandwidth": hostbw,
