@@ -1018,7 +1018,11 @@ extern __shared__ __align__(16) unsigned char gmc_smem[];
 // item only ever waits for an item drawn earlier, so the waits cannot deadlock.  A chain migrates between CTAs (and SMs):
 // its state is written with L2 stores + __threadfence() before the completion count is published, and read back only
 // through L2 (TMA bulk copies, ld.cg).
+#ifdef GMC_STEP_MAXNREG   // A/B: cap the 256-thread kernel below 128 registers so that small kernels fit next to two step CTAs
+__global__ void __maxnreg__(GMC_STEP_THREADS == 256 ? GMC_STEP_MAXNREG : 128)
+#else
 __global__ void __launch_bounds__(GMC_STEP_THREADS, GMC_STEP_MIN_CTAS)
+#endif
     run_kernel(GmcDev d, double* bed_all, double* mcres_all, double* ssq_all, const uint64_t* __restrict__ seeds,
                uint64_t iter0, int n_steps, double* loss_cache, uint8_t* step_cache, int32_t* blocks_cache,
                int64_t cache_stride, int64_t cache_offset, int32_t* resampled_all, int resync_every, int tile_off,
