@@ -77,6 +77,7 @@ def cpu_mp(a):
     def one(step, n_iter):
         out = tempfile.mkdtemp(prefix="gmc_ref_")
         seeds = [100000 + 1000 * step + c for c in range(cores)]          # str(seed)[:6] must be unique per chain
+        assert len({str(s)[:6] for s in seeds}) == cores, "chains would share a checkpoint folder and resume from each other"
         for s in seeds:
             os.makedirs(os.path.join(out, "LargeScaleChain", str(s)[:6]), exist_ok=True)
         t0 = time.perf_counter()
@@ -87,7 +88,7 @@ def cpu_mp(a):
         acc = float(np.mean([r[4].mean() for r in res]))
         return dt, acc
     for w in range(a.warmup):
-        one(900 + w, max(a.iters // 10, 3))
+        one(800 + w, max(a.iters // 10, 3))                               # 900000 + c: still six digits, so folders stay distinct
     times, acc = [], 0.0
     for s in range(max(a.steps, 1)):
         dt, acc = one(s, a.iters)

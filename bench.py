@@ -149,9 +149,12 @@ def cpu_arm(a, n_iter, steps, warmup):
                     f"(largeScaleChain_multiprocessing.py:19, one mp.Pool worker per chain, pool start-up and checkpoint I/O included), "
                     f"same {a.grid}x{a.grid} grid")
         sys.stderr.write(f"bench.py: reference driver unavailable ({r.get('unavailable')}); timing the oracle port instead\n")
+        why = f"; the reference driver was unavailable here: {str(r.get('unavailable'))[-160:]}"
+    else:
+        why = ""
     v, c, sps = port_arm(a.grid, n_iter, steps, warmup, cores)
     return (v, c, sps, "port", f"{c} chains x {n_iter} iterations per step, numpy port of chain_crf.run (oracle/crf_oracle.py), "
-                               f"one process per core, same {a.grid}x{a.grid} grid")
+                               f"one process per core, same {a.grid}x{a.grid} grid{why}")
 
 
 def reference_main(a):
