@@ -566,7 +566,7 @@ def gpu_main(a):
     stencil = {"U2_residual_loss": {"GBps": cells * 8 / (ms_u2 * 1e-3) / 1e9, "bytes_per_cell": 8, "ms": ms_u2},
                "U1_residual": {"GBps": cells * 16 / (ms_u1 * 1e-3) / 1e9, "bytes_per_cell": 16, "ms": ms_u1},
                "torch_copy_same_arrays": {"GBps": cells * 16 / (ms_cp * 1e-3) / 1e9, "ms": ms_cp}, "peak": peak,
-               "kernel": ctx.stencil_kernel_name(), "ncu": ncu_sidecar("residual_tma_kernel")}
+               "kernel": ctx.stencil_kernel_name(), "ncu": ncu_sidecar("residual_tma_kernel"), "ncu_U2": ncu_sidecar("residual_tma_kernel_U2")}
     for k in ("U2_residual_loss", "U1_residual", "torch_copy_same_arrays"):
         stencil[k]["frac"] = stencil[k]["GBps"] / peak
     del scratch_res

@@ -471,9 +471,9 @@ static int check_common(gmc_ctx* c, const void* p, int C, const char* who) {
 template <bool WR, bool LS, bool TST>
 static bool launch_tma_variant(gmc_ctx* c, cudaStream_t st, const double* bed, double* res, int C, double* partials) {
     CUtensorMap tm_bed, tm_out;
-    if (!r2_encode(&tm_bed, bed, C, c->H, c->W, R2_BOXW, R2_BOXH)) return false;
+    if (!r2_encode(&tm_bed, bed, C, c->H, c->W, R2_BOXW, R2_FETCH_ROWS)) return false;
     if (!r2_encode(&tm_out, WR ? res : bed, C, c->H, c->W, R2_TW, R2_RW)) return false;
-    const int smem = r2_layout(WR && TST, LS).total;
+    const int smem = r2_layout(WR && TST, LS, r2_stages(WR)).total;
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
         if (cudaFuncSetAttribute(residual_tma_kernel<WR, LS, TST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;

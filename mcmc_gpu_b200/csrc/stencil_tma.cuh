@@ -20,6 +20,12 @@
 #ifndef R2_STAGES
 #define R2_STAGES 8            // ring depth (tensor tiles in flight per CTA = R2_STAGES - R2_LAG)
 #endif
+#ifndef R2_LOSS_STAGES
+#define R2_LOSS_STAGES 6       // ring depth of the loss-only variant (smaller ring, more CTAs per SM)
+#endif
+#ifndef R2_LOSS_MIN_CTAS
+#define R2_LOSS_MIN_CTAS 5     // loss-only variant: 20 chain-independent doubles per lane, <= 96 registers
+#endif
 #ifndef R2_LAG
 #define R2_LAG 2               // the producer refills the stage consumed R2_LAG iterations ago
 #endif
@@ -32,8 +38,11 @@
 #define R2_TW 64
 #define R2_BOXW (R2_TW + 4)                      // 68 columns: [pad, haloL, 64 cells, haloR, pad]
 #define R2_BOXH (R2_TH + 2)
-#define R2_BOX_BYTES (R2_BOXH * R2_BOXW * 8)     // 5440
-#define R2_STAGE_BYTES ((R2_BOX_BYTES + 127) / 128 * 128)
+#ifndef R2_FETCH_ROWS
+#define R2_FETCH_ROWS R2_BOXH    // timing experiments only: fewer rows per tensor copy (wrong results) shows what the halo traffic costs
+#endif
+#define R2_BOX_BYTES (R2_FETCH_ROWS * R2_BOXW * 8)     // 5440
+#define R2_STAGE_BYTES ((R2_BOXH * R2_BOXW * 8 + 127) / 128 * 128)
 #define R2_THREADS (R2_WARPS * 32)
 #define R2_OUT_BUFS 4                            // per-warp staging buffers of the tensor stores
 #define R2_LS_IT 8                               // loss partials are transposed through shared memory every 8 chains
@@ -43,12 +52,13 @@
 struct R2Layout {                                // byte offsets inside the dynamic shared memory (128-byte aligned base)
     int bars, out, lsum, total;
 };
-__host__ __device__ inline R2Layout r2_layout(bool tma_store, bool do_loss) {
+__host__ __device__ constexpr int r2_stages(bool write_res) { return write_res ? R2_STAGES : R2_LOSS_STAGES; }
+__host__ __device__ inline R2Layout r2_layout(bool tma_store, bool do_loss, int n_stages) {
     const bool write_res = tma_store;
     R2Layout L;
-    int off = R2_STAGES * R2_STAGE_BYTES;
+    int off = n_stages * R2_STAGE_BYTES;
     L.bars = off;
-    off += 2 * R2_STAGES * 8;
+    off += 2 * n_stages * 8;
     off = (off + 127) / 128 * 128;
     L.out = off;
     if (write_res) off += R2_WARPS * R2_OUT_BUFS * R2_RW * R2_TW * 8;
@@ -225,6 +235,103 @@ __device__ __forceinline__ void r2_rows(const R2Lane& L, const GmcDev& d, unsign
     }
 }
 
+// ---- loss-only variant (nothing written back): the residual as a 5-point LINEAR form of the bed ---------------------
+// With f = v (surf - bed), the reference's cell residual (fxR - fxL) rdx + (fyD - fyU) rdy + dhdt - smb is
+//     r = K + cR bed_R + cL bed_L + cD bed_D + cU bed_U,
+//     K  = dhdt - smb + rdx (vxR surfR - vxL surfL) + rdy (vyD surfD - vyU surfU),
+//     cR = -rdx vxR,  cL = rdx vxL,  cD = -rdy vyD,  cU = rdy vyU
+// (R/L/D/U = the neighbours np.gradient uses: the cell itself on the one-sided edge rows / columns; rdx, rdy = 1/(2 res)
+// or 1/res there).  K and the four coefficients do not depend on the chain: a lane forms them once for its four cells (20
+// doubles instead of the 40 operands of the flux form), and a chain costs 4 fma + 1 square per cell — 24 FP64 instructions
+// per warp-iteration instead of 55.  The residual of this form differs from the flux form by rounding only (a few ulp of
+// the flux magnitude); it feeds nothing but the masked sum of squares, whose contract is 1e-9 relative (measured: ~1e-15).
+// Cells outside the loss mask (and outside the grid) get K = c = 0, so their square is exactly 0 and the common case needs
+// no per-cell select; a NaN anywhere in the lane's four squares takes the cold per-cell path (nan cells count 0).
+struct R2Lin {
+    double K[R2_RW][2], cL[R2_RW][2], cR[R2_RW][2], cU[R2_RW][2], cD[R2_RW][2];
+};
+
+template <bool EDGE>
+__device__ __forceinline__ void r2_lin_setup(R2Lin& Q, const R2Lane& L, double r_res, double r_two_res, bool xl_edge, bool xr_edge,
+                                             int k_top, int k_bot, unsigned mcbits) {
+#pragma unroll
+    for (int k = 0; k < R2_RW; ++k) {
+        // neighbours of the lane's two cells in row k: [surf, vel] left / right (x) and up / down (y)
+        double sL[2] = {L.sfl[k], L.sf[k + 1].x}, vL[2] = {L.vxl[k], L.vx[k].x};
+        double sR[2] = {L.sf[k + 1].y, L.sfr[k]}, vR[2] = {L.vx[k].y, L.vxr[k]};
+        double sU[2] = {L.sf[k].x, L.sf[k].y}, vU[2] = {L.vy[k].x, L.vy[k].y};
+        double sD[2] = {L.sf[k + 2].x, L.sf[k + 2].y}, vD[2] = {L.vy[k + 2].x, L.vy[k + 2].y};
+        double rdx[2] = {r_two_res, r_two_res}, rdy = r_two_res;
+        if (EDGE) {
+            if (xl_edge) { sL[0] = L.sf[k + 1].x; vL[0] = L.vx[k].x; rdx[0] = r_res; }
+            if (xr_edge) { sR[1] = L.sf[k + 1].y; vR[1] = L.vx[k].y; rdx[1] = r_res; }
+            if (k == k_top) { sU[0] = L.sf[k + 1].x; sU[1] = L.sf[k + 1].y; vU[0] = L.vy[k + 1].x; vU[1] = L.vy[k + 1].y; }
+            if (k == k_bot) { sD[0] = L.sf[k + 1].x; sD[1] = L.sf[k + 1].y; vD[0] = L.vy[k + 1].x; vD[1] = L.vy[k + 1].y; }
+            if (k == k_top || k == k_bot) rdy = r_res;
+        }
+        const double dhm[2] = {L.dh[k].x, L.dh[k].y};              // dhdt - smb (combined by the caller)
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            const bool on = (mcbits >> (2 * k + x)) & 1u;
+            const double gx = fma(vR[x], sR[x], -(vL[x] * sL[x])), gy = fma(vD[x], sD[x], -(vU[x] * sU[x]));
+            Q.K[k][x] = on ? fma(gx, rdx[x], fma(gy, rdy, dhm[x])) : 0.0;
+            Q.cR[k][x] = on ? -(rdx[x] * vR[x]) : 0.0;
+            Q.cL[k][x] = on ? rdx[x] * vL[x] : 0.0;
+            Q.cD[k][x] = on ? -(rdy * vD[x]) : 0.0;
+            Q.cU[k][x] = on ? rdy * vU[x] : 0.0;
+        }
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void r2_rows_lin(const R2Lin& Q, unsigned sa, bool xl_edge, bool xr_edge, int k_top, int k_bot,
+                                            double& acc, unsigned release_bar, int lane) {
+    double2 bd[R2_RW + 2];
+    double bl[R2_RW], br[R2_RW];
+#pragma unroll
+    for (int k = 0; k < R2_RW + 2; ++k)
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(bd[k].x), "=d"(bd[k].y) : "r"(sa + k * (R2_BOXW * 8)));
+    // (x-neighbours through warp shuffles instead of these 8-byte loads: 67 % instead of 74 % of the HBM peak at 4096 x 500^2 -
+    // profiles/r2/stencil_lin_ab.txt; the kernel sits at the shared-memory / MIO pipe's limit and shuffles queue there too)
+#pragma unroll
+    for (int k = 0; k < R2_RW; ++k) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bl[k]) : "r"(sa + (k + 1) * (R2_BOXW * 8) - 8));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(br[k]) : "r"(sa + (k + 1) * (R2_BOXW * 8) + 16));
+    }
+    __syncwarp();
+    if (lane == 0) r2_mbar_arrive(release_bar);                    // every lane has its operands: the stage may be refilled
+    double sq[R2_RW][2];
+#ifdef R2_EXPERIMENT_NOCOMPUTE                                     // timing experiments only: the tile stream without the arithmetic
+    acc = bd[1].x + bl[0] + br[1] + bd[3].y + bd[0].x + bd[2].y;
+    return;
+#endif
+#pragma unroll
+    for (int k = 0; k < R2_RW; ++k) {
+        double bL[2] = {bl[k], bd[k + 1].x}, bR[2] = {bd[k + 1].y, br[k]};
+        double bU[2] = {bd[k].x, bd[k].y}, bD[2] = {bd[k + 2].x, bd[k + 2].y};
+        if (EDGE) {
+            if (xl_edge) bL[0] = bd[k + 1].x;
+            if (xr_edge) bR[1] = bd[k + 1].y;
+            if (k == k_top) { bU[0] = bd[k + 1].x; bU[1] = bd[k + 1].y; }
+            if (k == k_bot) { bD[0] = bd[k + 1].x; bD[1] = bd[k + 1].y; }
+        }
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            const double r = fma(Q.cR[k][x], bR[x], fma(Q.cL[k][x], bL[x], fma(Q.cD[k][x], bD[x], fma(Q.cU[k][x], bU[x], Q.K[k][x]))));
+            sq[k][x] = mul_rn(r, r);
+        }
+    }
+    static_assert(R2_RW == 2, "the loss tree is written for two rows per warp");
+    acc = add_rn(add_rn(sq[0][0], sq[0][1]), add_rn(sq[1][0], sq[1][1]));
+    if (acc != acc) {                                              // cold: a nan cell somewhere; nan cells count 0, same tree
+#pragma unroll
+        for (int k = 0; k < R2_RW; ++k)
+#pragma unroll
+            for (int x = 0; x < 2; ++x) sq[k][x] = (sq[k][x] == sq[k][x]) ? sq[k][x] : 0.0;
+        acc = add_rn(add_rn(sq[0][0], sq[0][1]), add_rn(sq[1][0], sq[1][1]));
+    }
+}
+
 template <bool WRITE_RES, bool DO_LOSS, bool EDGE, bool TMA_STORE>
 __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const CUtensorMap* tm_out, const GmcDev& d,
                                               unsigned char* smem, double* __restrict__ res_all, double* __restrict__ partials,
@@ -233,9 +340,10 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
     const int tid = threadIdx.x, warp = tid >> 5;
     int lane;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
-    const R2Layout lay = r2_layout(WRITE_RES && TMA_STORE, DO_LOSS);
+    constexpr int NS = r2_stages(WRITE_RES);        // ring depth of this variant
+    const R2Layout lay = r2_layout(WRITE_RES && TMA_STORE, DO_LOSS, NS);
     const unsigned stage0 = r2_smem_u32(smem);
-    const unsigned bars = stage0 + lay.bars;      // full[s] at bars + 8 s, empty[s] at bars + 8 (R2_STAGES + s)
+    const unsigned bars = stage0 + lay.bars;      // full[s] at bars + 8 s, empty[s] at bars + 8 (NS + s)
     const int tx0 = blockIdx.x * R2_TW, ty0 = blockIdx.y * R2_TH;
     const int i0 = ty0 + warp * R2_RW;            // first grid row of this warp
     const int c0 = tx0 + 2 * lane;                // first grid column of this lane
@@ -243,16 +351,16 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
     const int n_iter = (C - (int)blockIdx.z + G - 1) / G;
 
     if (tid == 0) {
-        for (int s = 0; s < R2_STAGES; ++s) {
+        for (int s = 0; s < NS; ++s) {
             r2_mbar_init(bars + 8 * s, 1);
-            r2_mbar_init(bars + 8 * (R2_STAGES + s), R2_WARPS);
+            r2_mbar_init(bars + 8 * (NS + s), R2_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // prologue of the ring: R2_STAGES - R2_LAG tiles in flight before anything else is fetched
+    // prologue of the ring: NS - R2_LAG tiles in flight before anything else is fetched
     if (tid == 0) {
-        for (int s = 0; s < R2_STAGES - R2_LAG && s < n_iter; ++s) {
+        for (int s = 0; s < NS - R2_LAG && s < n_iter; ++s) {
             r2_mbar_expect_tx(bars + 8 * s, R2_BOX_BYTES);
             r2_tma_load3(stage0 + s * R2_STAGE_BYTES, tm_bed, tx0 - 2, ty0 - 1, (int)blockIdx.z + s * G, bars + 8 * s);
         }
@@ -305,6 +413,8 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
     bool vrow[R2_RW];
 #pragma unroll
     for (int k = 0; k < R2_RW; ++k) vrow[k] = !EDGE || (vcol && i0 + k < H);
+    R2Lin Q;
+    if (!WRITE_RES) r2_lin_setup<EDGE>(Q, L, r_res, r_two_res, xl_edge, xr_edge, k_top, k_bot, mcbits);   // L is dead after this
 
     const unsigned lane_sa = stage0 + (unsigned)((warp * R2_RW) * R2_BOXW + 2 + 2 * lane) * 8u;   // stage 0, this lane's halo-row pair
     const int tile_id = (blockIdx.y * R2_WARPS + warp) * gridDim.x + blockIdx.x;
@@ -324,21 +434,24 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
     for (int it = 0; it < n_iter; ++it) {
         // ---- producer (warp 0): refill the stage consumed R2_LAG iterations ago with the tile of chain it+STAGES-LAG ----
         if (warp == 0) {
-            if (lane == 0 && it + R2_STAGES - R2_LAG < n_iter) {
+            if (lane == 0 && it + NS - R2_LAG < n_iter) {
                 int ps = s - R2_LAG;
                 unsigned pph = phase;
-                if (ps < 0) { ps += R2_STAGES; pph ^= 1u; }
-                if (it >= R2_LAG) r2_mbar_wait(bars + 8 * (R2_STAGES + ps), pph);             // all four warps released it
+                if (ps < 0) { ps += NS; pph ^= 1u; }
+                if (it >= R2_LAG) r2_mbar_wait(bars + 8 * (NS + ps), pph);             // all four warps released it
                 r2_mbar_expect_tx(bars + 8 * ps, R2_BOX_BYTES);
-                r2_tma_load3(stage0 + ps * R2_STAGE_BYTES, tm_bed, tx0 - 2, ty0 - 1, zc + (R2_STAGES - R2_LAG) * G, bars + 8 * ps);
+                r2_tma_load3(stage0 + ps * R2_STAGE_BYTES, tm_bed, tx0 - 2, ty0 - 1, zc + (NS - R2_LAG) * G, bars + 8 * ps);
             }
             __syncwarp();
         }
         r2_mbar_wait(bars + 8 * s, phase);
         double2 r[R2_RW];
         double acc;
-        r2_rows<DO_LOSS, EDGE, WRITE_RES>(L, d, lane_sa + s * R2_STAGE_BYTES, r_res, r_two_res, xl_edge, xr_edge, k_top, k_bot, vrow, mcbits, r, acc,
-                               bars + 8 * (R2_STAGES + s), lane);
+        if (WRITE_RES)
+            r2_rows<DO_LOSS, EDGE, true>(L, d, lane_sa + s * R2_STAGE_BYTES, r_res, r_two_res, xl_edge, xr_edge, k_top, k_bot, vrow, mcbits, r, acc,
+                                         bars + 8 * (NS + s), lane);
+        else
+            r2_rows_lin<EDGE>(Q, lane_sa + s * R2_STAGE_BYTES, xl_edge, xr_edge, k_top, k_bot, acc, bars + 8 * (NS + s), lane);
         if (WRITE_RES) {
             if (TMA_STORE) {
                 // the warp's 2 x 64 residual tile -> its staging buffer -> one tensor store (clipped at the grid edge by TMA)
@@ -380,7 +493,7 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
             pp += pstride;
         }
         zc += G;
-        if (++s == R2_STAGES) { s = 0; phase ^= 1u; }
+        if (++s == NS) { s = 0; phase ^= 1u; }
     }
     if (WRITE_RES && TMA_STORE) {
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before the CTA exits
@@ -388,7 +501,7 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
 }
 
 template <bool WRITE_RES, bool DO_LOSS, bool TMA_STORE>
-__global__ void __launch_bounds__(R2_THREADS, (WRITE_RES ? R2_MIN_CTAS : R2_MIN_CTAS + 1))   // the loss-only variant fits 128 registers
+__global__ void __launch_bounds__(R2_THREADS, (WRITE_RES ? R2_MIN_CTAS : R2_LOSS_MIN_CTAS))
     residual_tma_kernel(const __grid_constant__ CUtensorMap tm_bed, const __grid_constant__ CUtensorMap tm_out, GmcDev d,
                         double* __restrict__ res_all, double* __restrict__ partials, int n_tiles, int C, double r_res,
                         double r_two_res) {

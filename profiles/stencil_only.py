@@ -28,3 +28,7 @@ for name, fn, b in (("U1 residual (8 B read + 8 B write / cell)", lambda: ctx.re
                     ("torch copy (8 B read + 8 B write / cell)", lambda: res.copy_(bed), 16)):
     ms = t(fn)
     print(f"{name:45s} {ms:8.4f} ms  {cells * b / ms / 1e6:8.1f} GB/s  ({cells * b / ms / 1e6 / 6545.6 * 100:5.1f}% of measured 6545.6 GB/s)")
+# the loss-only variant evaluates the residual as a linear form of the bed: its loss against the exact (bit-identical) residual's
+ctx.residual_loss(bed, None, loss, None); l_lin = loss.cpu().numpy().copy()
+ctx.residual(bed, res); ctx.loss(res, loss); l_exact = loss.cpu().numpy()
+print(f"loss-only (linear form) vs loss of the exact residual: max relative difference {np.abs(l_lin / l_exact - 1).max():.2e}")
