@@ -75,6 +75,48 @@ def test_batched_residual_and_loss(H, W, C):
     assert np.allclose(ssq_d.cpu().numpy() / (2 * sigma ** 2), loss_fused, rtol=1e-15)
 
 
+def test_loss_only_linear_form_agrees_with_the_exact_residual():
+    """The loss-only stencil variant evaluates the residual as a 5-point linear form of the bed (csrc/stencil_tma.cuh,
+    R2Lin); the variants that write the residual keep the flux form.  Same loss to 1e-12 (contract 1e-9) over a wide
+    dynamic range of velocities, nan statics, nan / inf bed cells, a sparse loss mask and every edge rule."""
+    import torch
+    from mcmc_gpu_b200._lib import Context
+    H, W, C = 97, 192, 12
+    g = np.random.default_rng(11)
+    surf = 1500.0 + 300.0 * g.standard_normal((H, W))
+    velx = g.standard_normal((H, W)) * 10.0 ** g.uniform(-3, 3, (H, W))
+    vely = g.standard_normal((H, W)) * 10.0 ** g.uniform(-3, 3, (H, W))
+    velx[g.random((H, W)) < 0.02] = np.nan
+    vely[0, :7] = 0.0
+    dhdt, smb = g.standard_normal((H, W)), g.standard_normal((H, W))
+    mask = (g.random((H, W)) < 0.35).astype(np.uint8)
+    mask[0, :], mask[-1, :], mask[:, 0], mask[:, -1] = 1, 1, 1, 1           # the one-sided rows / columns count
+    mask[50, 99], velx[50, 98:103] = 1, 3.0                                   # a counted neighbour of the infinite bed cell below
+    beds = surf[None] - 900.0 + 200.0 * g.standard_normal((C, H, W))
+    beds[1, 40, 60] = np.nan
+    beds[2, 0, 0] = beds[2, H - 1, W - 1] = np.nan
+    beds[3, 50, 100] = np.inf                                                 # an infinite residual is an infinite loss
+    sigma, res_m = 2.0, 500.0
+    ctx = Context(H, W, C)
+    ctx.set_static(surf, velx, vely, dhdt, smb, np.ones((H, W)), mask, None, None, res_m, sigma)
+    assert "tma" in ctx.stencil_kernel_name()
+    bed_d = torch.as_tensor(beds).cuda()
+    res_d = torch.empty_like(bed_d)
+    lin, exact = (torch.empty(C, dtype=torch.float64, device="cuda") for _ in range(2))
+    ctx.residual_loss(bed_d, None, lin, None)                                 # loss-only: linear form
+    ctx.residual_loss(bed_d, res_d, exact, None)                              # residual written: flux form, exact division
+    lin, exact = lin.cpu().numpy(), exact.cpu().numpy()
+    with np.errstate(all="ignore"):
+        for c in range(C):
+            ref = O.mass_conservation_residual(beds[c], surf, velx, vely, dhdt, smb, res_m)
+            ref_loss = O.masked_loss(ref, mask, sigma)[0]
+            if np.isinf(ref_loss):
+                assert c == 3 and np.isinf(lin[c]) and np.isinf(exact[c])
+                continue
+            assert abs(exact[c] - ref_loss) <= 1e-12 * ref_loss
+            assert abs(lin[c] - ref_loss) <= 1e-12 * ref_loss, (c, lin[c], ref_loss)
+
+
 def test_signed_zero_and_special_quotients_are_bit_identical():
     """Zero thickness makes every flux +-0, so every quotient is +-0 (sign from the velocities); with dhdt = -0 the
     sign survives into the residual.  Also huge / tiny / infinite fluxes, which leave the fast division path."""
