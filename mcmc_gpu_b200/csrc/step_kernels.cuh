@@ -873,6 +873,8 @@ __device__ void step_tail(const GmcDev& d, StepScalars* sc, double* scratch, con
     // prepares the next step instead (and warp 14 of the wide CTA idles here)
     constexpr int B_THREADS = GMC_TAIL_WORKERS;
     if (HELPER && threadIdx.x >= GMC_STEP_THREADS - 32) prepare_step(d, rng, next->it, *next->sc, *next->pair, *next->tab, next->vec);
+    // (unrolling this loop by two so that the loads of two trips overlap measured 4 % SLOWER at 128 registers: 6.12 vs 6.38 M
+    // chain-steps/s at 256 x 500^2 - profiles/r2/step_ab.txt)
     for (int e = (threadIdx.x >= B_THREADS) ? bh * bw : threadIdx.x; e < bh * bw; e += B_THREADS, ++trip) {
         const int bi = dbw.div(e), bj = e - bi * bw;
         const int i = s.x0 + bi, j = s.y0 + bj;
