@@ -430,9 +430,32 @@ def sgs_sample(a, dev, fp64_peak):
     ms = e0.elapsed_time(e1)
     nodes = float((bl[..., 2].astype(np.float64) * bl[..., 3]).sum())
     batch.close()
+    # the same through the public objects with HOST arrays on both sides: C initial beds up (pinned), n_it iterations, the
+    # final beds and the loss / accept / block caches down - set-up of the batch (normal scores, residual) inside the timed region
+    beds_host = torch.empty((C, H, W), dtype=torch.float64).pin_memory()
+    beds_host.copy_(torch.as_tensor(bed)[None].expand(C, H, W))
+    keys = [MCMC.philox_key(s) for s in range(C)]
+    out_host = torch.empty((C, H, W), dtype=torch.float64).pin_memory()
+
+    def e2e_once():
+        b = MCMC.SgsBatch(ch, beds_host.numpy(), keys, device=dev)
+        caches = b.advance(n_it)
+        final = b.beds(out=out_host)
+        b.close()
+        return final, caches
+    e2e_once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    final, caches = e2e_once()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e = {"value": C * n_it / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": int(beds_host.numel() * 8),
+           "d2h_bytes_per_step": int(final.nbytes + sum(x.nbytes for x in caches)),
+           "what": "MCMC.SgsBatch(pinned host beds) -> advance(iters) -> beds(out=pinned) on the host, wall clock, batch set-up included"}
+    del final, caches, beds_host, out_host
     out = {"workload": f"small-scale SGS chain, {C} chains, 300x300, blocks 5-19, 48 neighbours, radius 30 km, Matern nu=1.2259",
            "chain_steps_per_s": C * n_it / (ms * 1e-3), "kriged_nodes_per_s": nodes / (ms * 1e-3), "iters": n_it, "ms": ms,
-           "acceptance_rate": float(st.mean())}
+           "acceptance_rate": float(st.mean()), "e2e": e2e}
     # FP64 work of the kriging solves: Gauss-Jordan on the augmented 49 x 51 system = ~n^2 (n+2) FMA per node (n = 49)
     n = 49
     flops = 2.0 * n * n * (n + 2) * nodes

@@ -728,21 +728,14 @@ class SgsBatch:
         # round-trips only the accepted block.  The two agree (to the transform's own <= 1e-12 round-trip drift) exactly
         # when no detrended cell lies outside that range - true for a transformer fitted on initial_bed - trend as in the
         # reference's scripts, not for one fitted on the conditioning data alone.
-        if getattr(chain_obj, "do_transform", False) and getattr(chain_obj, "nst_trans", None) is not None:
-            q = np.asarray(chain_obj.nst_trans.quantiles_[:, 0], dtype=np.float64)
-            base = beds - (np.asarray(chain_obj.trend, dtype=np.float64)[None] if chain_obj.detrend_map else 0.0)
-            n_out = int(np.count_nonzero((base < q[0]) | (base > q[-1])))
-            if n_out:
-                import warnings
-                warnings.warn(f"chain_sgs: {n_out} detrended bed cells lie outside the normal-score transformer's fitted range "
-                              f"[{q[0]:.6g}, {q[-1]:.6g}]; the reference clamps such cells to that range at its first accepted "
-                              "step (MCMC.py:1767-1806) while this kernel leaves cells outside the proposed blocks untouched, "
-                              "so the trajectories differ there.  Fit the transformer on initial_bed - trend (as the reference's "
-                              "drivers do) or clip the initial beds to the fitted range.", RuntimeWarning, stacklevel=3)
-        # NaN cells in the beds are unconditioned cells outside the block: a node may then find nothing within the radius
-        self.ctx = chain_obj._sgs_context(self.C, device, widen=bool(np.isnan(beds).any()))
-        dev = self.dev = self.ctx.device
+        check_range = getattr(chain_obj, "do_transform", False) and getattr(chain_obj, "nst_trans", None) is not None
+        from ._lib import require_cuda
+        dev = require_cuda(device)
         full = torch.as_tensor(beds).to(dev)
+        # NaN cells in the beds are unconditioned cells outside the block: a node may then find nothing within the radius
+        # (looked for on the device: a host pass over C x H x W doubles costs more than the upload)
+        self.ctx = chain_obj._sgs_context(self.C, device, widen=bool(torch.isnan(full).any().item()))
+        dev = self.dev = self.ctx.device
         self.bedc = torch.empty_like(full)
         self.z = torch.empty_like(full)
         self.mcres = torch.empty_like(full)
@@ -753,6 +746,18 @@ class SgsBatch:
         self.seeds = keys_tensor(keys, dev)
         self.iteration = int(iter0)
         self.trend = None if not chain_obj.detrend_map else torch.as_tensor(np.ascontiguousarray(chain_obj.trend, dtype=np.float64)).to(dev)
+        if check_range:                                            # counted on the device: the beds are already there
+            q = np.asarray(chain_obj.nst_trans.quantiles_[:, 0], dtype=np.float64)
+            base = full - self.trend if self.trend is not None else full
+            n_out = int(((base < float(q[0])) | (base > float(q[-1]))).sum().item())
+            del base
+            if n_out:
+                import warnings
+                warnings.warn(f"chain_sgs: {n_out} detrended bed cells lie outside the normal-score transformer's fitted range "
+                              f"[{q[0]:.6g}, {q[-1]:.6g}]; the reference clamps such cells to that range at its first accepted "
+                              "step (MCMC.py:1767-1806) while this kernel leaves cells outside the proposed blocks untouched, "
+                              "so the trajectories differ there.  Fit the transformer on initial_bed - trend (as the reference's "
+                              "drivers do) or clip the initial beds to the fitted range.", RuntimeWarning, stacklevel=3)
         scratch = torch.empty_like(full)
         self.ctx.sgs_init(full, self.bedc, self.z, self.mcres, self.ssq, self.nviol, scratch)
 
@@ -768,8 +773,12 @@ class SgsBatch:
         den = self.torch.full_like(self.ssq, 2 * self.chain.sigma_mc ** 2)
         return (self.ssq / den).cpu().numpy()
 
-    def beds(self, with_trend=True):
+    def beds(self, with_trend=True, out=None):
+        """Final beds on the host; `out` (a pinned [C,H,W] float64 tensor) receives them without a pageable staging copy."""
         b = self.bedc + self.trend if (with_trend and self.trend is not None) else self.bedc
+        if out is not None:
+            out.copy_(b)
+            return out.numpy()
         return b.cpu().numpy()
 
     def resampled_times(self):

@@ -83,6 +83,12 @@ def test_free_run_is_batch_invariant_and_sane():
     loss = torch.empty(4, dtype=torch.float64, device="cuda")
     a.ctx.residual_loss(full, None, loss, None)
     assert np.allclose(loss.cpu().numpy(), la[:, -1], rtol=1e-9, atol=0)
+    # pinned host tensors in and out (the end-to-end path of bench.py's sgs.e2e) give the same beds
+    pinned_in = torch.as_tensor(beds0).pin_memory()
+    pinned_out = torch.empty_like(pinned_in).pin_memory()
+    c = MCMC.SgsBatch(ch, pinned_in.numpy(), keys)
+    c.advance(25)
+    assert bits_equal(c.beds(out=pinned_out), a.beds())
 
 
 def test_public_run_api_free_rng():
