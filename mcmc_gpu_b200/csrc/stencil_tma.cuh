@@ -26,6 +26,9 @@
 #ifndef R2_LOSS_MIN_CTAS
 #define R2_LOSS_MIN_CTAS 5     // loss-only variant: 20 chain-independent doubles per lane, <= 96 registers
 #endif
+#ifndef R2_LIN4
+#define R2_LIN4 1             // loss-only variant: a lane owns 4 rows x 1 column (1) or 2 rows x 2 columns (0)
+#endif
 #ifndef R2_LAG
 #define R2_LAG 2               // the producer refills the stage consumed R2_LAG iterations ago
 #endif
@@ -332,6 +335,82 @@ __device__ __forceinline__ void r2_rows_lin(const R2Lin& Q, unsigned sa, bool xl
     }
 }
 
+// ---- the same linear form with a lane owning 4 rows x 1 column (warp: 4 rows x 32 columns, CTA tile 8 x 64 as 2 x 2 warps) ---
+// The variant is bound by shared-memory wavefronts, not by arithmetic (ncu: 68 % of the pipe's peak, short_scoreboard the top
+// stall).  With 2 x 2 cells per lane the x-neighbours are 8-byte loads at a 16-byte lane stride - 4 wavefronts for 256
+// useful bytes - and a warp reads 4 rows to produce 2: 32 wavefronts per 128 cells.  With 4 x 1 cells per lane every access
+// is a fully coalesced 8-byte load (2 wavefronts) and a warp reads 6 rows to produce 4: 6 + 8 loads = 28 wavefronts per 128
+// cells, same 20 coefficients per lane.  The coefficients come straight from global memory in the CTA prologue.
+struct R2Lin4 {
+    double K[4], cL[4], cR[4], cU[4], cD[4];
+};
+
+template <bool EDGE>
+__device__ __forceinline__ void r2_lin4_setup(R2Lin4& Q, const GmcDev& d, int i0, int j, double r_res, double r_two_res) {
+    const int H = d.H, W = d.W;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k;
+        double K = 0.0, cL = 0.0, cR = 0.0, cU = 0.0, cD = 0.0;
+        if (!EDGE || (i < H && j < W)) {
+            const int64_t idx = (int64_t)i * W + j;
+            if (__ldg(d.flags + idx) & FLAG_MC) {
+                const bool xl = EDGE && j == 0, xr = EDGE && j == W - 1, top = EDGE && i == 0, bot = EDGE && i == H - 1;
+                const int64_t iL = xl ? idx : idx - 1, iR = xr ? idx : idx + 1, iU = top ? idx : idx - W, iD = bot ? idx : idx + W;
+                const double sL = __ldg(d.surf + iL), vL = __ldg(d.velx + iL), sR = __ldg(d.surf + iR), vR = __ldg(d.velx + iR);
+                const double sU = __ldg(d.surf + iU), vU = __ldg(d.vely + iU), sD = __ldg(d.surf + iD), vD = __ldg(d.vely + iD);
+                const double rdx = (xl || xr) ? r_res : r_two_res, rdy = (top || bot) ? r_res : r_two_res;
+                const double dhm = __ldg(d.dhdt + idx) - __ldg(d.smb + idx);
+                const double gx = fma(vR, sR, -(vL * sL)), gy = fma(vD, sD, -(vU * sU));
+                K = fma(gx, rdx, fma(gy, rdy, dhm));
+                cR = -(rdx * vR);
+                cL = rdx * vL;
+                cD = -(rdy * vD);
+                cU = rdy * vU;
+            }
+        }
+        Q.K[k] = K;
+        Q.cL[k] = cL;
+        Q.cR[k] = cR;
+        Q.cU[k] = cU;
+        Q.cD[k] = cD;
+    }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void r2_rows_lin4(const R2Lin4& Q, unsigned sa, bool xl_edge, bool xr_edge, int k_top, int k_bot,
+                                             double& acc, unsigned release_bar, int lane) {
+    double bd[6], bl[4], br[4];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bd[m]) : "r"(sa + m * (R2_BOXW * 8)));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(bl[k]) : "r"(sa + (k + 1) * (R2_BOXW * 8) - 8));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(br[k]) : "r"(sa + (k + 1) * (R2_BOXW * 8) + 8));
+    }
+    __syncwarp();
+    if (lane == 0) r2_mbar_arrive(release_bar);                    // every lane has its operands: the stage may be refilled
+    double sq[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double bL = bl[k], bR = br[k], bU = bd[k], bD = bd[k + 2];
+        if (EDGE) {
+            if (xl_edge) bL = bd[k + 1];
+            if (xr_edge) bR = bd[k + 1];
+            if (k == k_top) bU = bd[k + 1];
+            if (k == k_bot) bD = bd[k + 1];
+        }
+        const double r = fma(Q.cR[k], bR, fma(Q.cL[k], bL, fma(Q.cD[k], bD, fma(Q.cU[k], bU, Q.K[k]))));
+        sq[k] = mul_rn(r, r);
+    }
+    acc = add_rn(add_rn(sq[0], sq[1]), add_rn(sq[2], sq[3]));
+    if (acc != acc) {                                              // cold: a nan cell somewhere; nan cells count 0, same tree
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sq[k] = (sq[k] == sq[k]) ? sq[k] : 0.0;
+        acc = add_rn(add_rn(sq[0], sq[1]), add_rn(sq[2], sq[3]));
+    }
+}
+
 template <bool WRITE_RES, bool DO_LOSS, bool EDGE, bool TMA_STORE>
 __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const CUtensorMap* tm_out, const GmcDev& d,
                                               unsigned char* smem, double* __restrict__ res_all, double* __restrict__ partials,
@@ -369,7 +448,8 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
     // ---- the lane's chain-independent operands, straight from global memory (one exposed latency, behind the tiles) ----
     R2Lane L;
     const bool vcol = !EDGE || c0 < W;
-    {
+    constexpr bool LIN4 = !WRITE_RES && (R2_LIN4 != 0);           // loss-only variant with the 4 x 1 lane layout
+    if (!LIN4) {
         const double2 z2 = make_double2(0.0, 0.0);
 #pragma unroll
         for (int k = 0; k < R2_RW + 2; ++k) {
@@ -414,7 +494,15 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
 #pragma unroll
     for (int k = 0; k < R2_RW; ++k) vrow[k] = !EDGE || (vcol && i0 + k < H);
     R2Lin Q;
-    if (!WRITE_RES) r2_lin_setup<EDGE>(Q, L, r_res, r_two_res, xl_edge, xr_edge, k_top, k_bot, mcbits);   // L is dead after this
+    if (!WRITE_RES && !LIN4) r2_lin_setup<EDGE>(Q, L, r_res, r_two_res, xl_edge, xr_edge, k_top, k_bot, mcbits);   // L is dead after this
+    static_assert(R2_WARPS == 4 && R2_TH == 8 && R2_TW == 64, "the 4 x 1 lane layout tiles 8 x 64 cells as 2 x 2 warps");
+    R2Lin4 Q4;
+    const int i04 = ty0 + 4 * (warp >> 1), j4 = tx0 + 32 * (warp & 1) + lane;      // first row / the column of this lane
+    const bool xl4 = EDGE && j4 == 0, xr4 = EDGE && j4 == W - 1;
+    const int kt4 = (EDGE && i04 == 0) ? 0 : -1;
+    const int kb4 = (EDGE && H - 1 >= i04 && H - 1 < i04 + 4) ? H - 1 - i04 : -1;
+    const unsigned sa4 = stage0 + (unsigned)((4 * (warp >> 1)) * R2_BOXW + 2 + 32 * (warp & 1) + lane) * 8u;
+    if (LIN4) r2_lin4_setup<EDGE>(Q4, d, i04, j4, r_res, r_two_res);
 
     const unsigned lane_sa = stage0 + (unsigned)((warp * R2_RW) * R2_BOXW + 2 + 2 * lane) * 8u;   // stage 0, this lane's halo-row pair
     const int tile_id = (blockIdx.y * R2_WARPS + warp) * gridDim.x + blockIdx.x;
@@ -451,7 +539,8 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
             r2_rows<DO_LOSS, EDGE, true>(L, d, lane_sa + s * R2_STAGE_BYTES, r_res, r_two_res, xl_edge, xr_edge, k_top, k_bot, vrow, mcbits, r, acc,
                                          bars + 8 * (NS + s), lane);
         else
-            r2_rows_lin<EDGE>(Q, lane_sa + s * R2_STAGE_BYTES, xl_edge, xr_edge, k_top, k_bot, acc, bars + 8 * (NS + s), lane);
+            if (LIN4) r2_rows_lin4<EDGE>(Q4, sa4 + s * R2_STAGE_BYTES, xl4, xr4, kt4, kb4, acc, bars + 8 * (NS + s), lane);
+            else r2_rows_lin<EDGE>(Q, lane_sa + s * R2_STAGE_BYTES, xl_edge, xr_edge, k_top, k_bot, acc, bars + 8 * (NS + s), lane);
         if (WRITE_RES) {
             if (TMA_STORE) {
                 // the warp's 2 x 64 residual tile -> its staging buffer -> one tensor store (clipped at the grid edge by TMA)
