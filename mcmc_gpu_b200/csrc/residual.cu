@@ -488,12 +488,18 @@ static bool launch_tma_variant(gmc_ctx* c, cudaStream_t st, const double* bed, d
     // at most ~48 chains per CTA: CTAs of vertically adjacent tiles share two halo rows through L2 only while they work on
     // the same chains at about the same time; over hundreds of chains they drift apart and the halo rows come from DRAM
     // again (measured: 4096 chains in 7 groups 72 % of the HBM peak vs 82 % for 256 chains in 7 groups)
-    const int g_min = std::max(1, (C + 47) / 48);
+    // The loss-only variant (WR = false) forms its 20 coefficients per lane from ~44 scalar loads: its prologue costs about four
+    // chain-iterations, and longer CTAs pay (sweeps in profiles/r2/stencil_lin_ab.txt: 4096 chains 81 % of the HBM peak with 43
+    // groups of 95 chains, 78 % with 86 groups of 48), so its cap is 96 chains per CTA.
+    const int cap = WR ? 48 : 96;
+    const double prologue = WR ? 1.0 : 4.0;
+    const int g_min = std::max(1, (C + cap - 1) / cap);
     for (int G = g_min; G <= std::max(g_min, std::min(C / 4, 4096)); ++G) {
-        // cost model fitted to the sweeps in profiles/r2/stencil_groups.txt: a CTA's prologue costs about one chain-iteration,
-        // and the tail of the grid about one CTA duration (CTAs differ: boundary tiles, the producer warp), i.e. 1 / waves
+        // cost model fitted to the sweeps in profiles/r2/stencil_groups.txt: a CTA's prologue costs about one chain-iteration
+        // (four for the loss-only variant), and the tail of the grid about one CTA duration (CTAs differ: boundary tiles,
+        // the producer warp), i.e. 1 / waves
         const double n = (double)C / G, waves = (double)tx * ty * G / slots;
-        const double score = n / (n + 1.0) * waves / (waves + 1.0);
+        const double score = n / (n + prologue) * waves / (waves + 1.0);
         if (score > best + 1e-9) {
             best = score;
             groups = G;
