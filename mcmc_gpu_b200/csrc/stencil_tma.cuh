@@ -340,7 +340,7 @@ __device__ __forceinline__ void r2_rows_lin(const R2Lin& Q, unsigned sa, bool xl
 // stall).  With 2 x 2 cells per lane the x-neighbours are 8-byte loads at a 16-byte lane stride - 4 wavefronts for 256
 // useful bytes - and a warp reads 4 rows to produce 2: 32 wavefronts per 128 cells.  With 4 x 1 cells per lane every access
 // is a fully coalesced 8-byte load (2 wavefronts) and a warp reads 6 rows to produce 4: 6 + 8 loads = 28 wavefronts per 128
-// cells, same 20 coefficients per lane.  The coefficients come straight from global memory in the CTA prologue.
+// cells, same 20 coefficients per lane.  The coefficients are formed from global memory in the CTA prologue.
 struct R2Lin4 {
     double K[4], cL[4], cR[4], cU[4], cD[4];
 };
@@ -348,25 +348,35 @@ struct R2Lin4 {
 template <bool EDGE>
 __device__ __forceinline__ void r2_lin4_setup(R2Lin4& Q, const GmcDev& d, int i0, int j, double r_res, double r_two_res) {
     const int H = d.H, W = d.W;
+    // 16-byte loads of the packed statics ({surf, velx}, {surf, vely}, {dhdt, smb} per cell, built by gmc_set_static for the
+    // step kernel): the lane's column of {surf, vely} for rows i0-1 .. i0+4 once, then per cell its two x-neighbours and its
+    // own {dhdt, smb} - 22 loads per lane.  Rows / columns outside the grid are never used: the edge rules replace them.
+    const bool vcol = !EDGE || j < W;
+    double2 cy[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) {
+        const int i = i0 - 1 + m;
+        cy[m] = (vcol && (!EDGE || (i >= 0 && i < H))) ? __ldg(d.sy + (int64_t)i * W + j) : make_double2(0.0, 0.0);
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int i = i0 + k;
         double K = 0.0, cL = 0.0, cR = 0.0, cU = 0.0, cD = 0.0;
-        if (!EDGE || (i < H && j < W)) {
+        if (!EDGE || (i < H && vcol)) {
             const int64_t idx = (int64_t)i * W + j;
             if (__ldg(d.flags + idx) & FLAG_MC) {
                 const bool xl = EDGE && j == 0, xr = EDGE && j == W - 1, top = EDGE && i == 0, bot = EDGE && i == H - 1;
-                const int64_t iL = xl ? idx : idx - 1, iR = xr ? idx : idx + 1, iU = top ? idx : idx - W, iD = bot ? idx : idx + W;
-                const double sL = __ldg(d.surf + iL), vL = __ldg(d.velx + iL), sR = __ldg(d.surf + iR), vR = __ldg(d.velx + iR);
-                const double sU = __ldg(d.surf + iU), vU = __ldg(d.vely + iU), sD = __ldg(d.surf + iD), vD = __ldg(d.vely + iD);
+                const double2 xL = __ldg(d.sv + (xl ? idx : idx - 1)), xR = __ldg(d.sv + (xr ? idx : idx + 1));   // {surf, velx}
+                const double2 yU = top ? cy[k + 1] : cy[k], yD = bot ? cy[k + 1] : cy[k + 2];                       // {surf, vely}
+                const double2 hs = __ldg(d.ds + idx);                                                             // {dhdt, smb}
                 const double rdx = (xl || xr) ? r_res : r_two_res, rdy = (top || bot) ? r_res : r_two_res;
-                const double dhm = __ldg(d.dhdt + idx) - __ldg(d.smb + idx);
-                const double gx = fma(vR, sR, -(vL * sL)), gy = fma(vD, sD, -(vU * sU));
+                const double dhm = hs.x - hs.y;
+                const double gx = fma(xR.y, xR.x, -(xL.y * xL.x)), gy = fma(yD.y, yD.x, -(yU.y * yU.x));
                 K = fma(gx, rdx, fma(gy, rdy, dhm));
-                cR = -(rdx * vR);
-                cL = rdx * vL;
-                cD = -(rdy * vD);
-                cU = rdy * vU;
+                cR = -(rdx * xR.y);
+                cL = rdx * xL.y;
+                cD = -(rdy * yD.y);
+                cU = rdy * yU.y;
             }
         }
         Q.K[k] = K;
