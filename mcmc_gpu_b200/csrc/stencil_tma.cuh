@@ -49,6 +49,9 @@
 #define R2_THREADS (R2_WARPS * 32)
 #define R2_OUT_BUFS 4                            // per-warp staging buffers of the tensor stores
 #define R2_LS_IT 8                               // loss partials are transposed through shared memory every 8 chains
+#define R2_LS_PITCH 36                           // row pitch of that scratch (doubles), = 4 mod 16: lane (rr, qd) sums the entries qd + 4 j of
+                                                 // row rr, so the 16 lanes of a half-warp read 16 different 8-byte banks (4 rr + qd); with
+                                                 // pitch 33 and contiguous octets per lane every read was a 2-way bank conflict
 #define R2_DIV_LO2 (2u * 0x05d00000u)            // 2 * hi word of 2^-930
 #define R2_DIV_WIN (2u * (0x7a100000u - 0x05d00000u))
 
@@ -66,7 +69,7 @@ __host__ __device__ inline R2Layout r2_layout(bool tma_store, bool do_loss, int 
     L.out = off;
     if (write_res) off += R2_WARPS * R2_OUT_BUFS * R2_RW * R2_TW * 8;
     L.lsum = off;
-    if (do_loss) off += R2_WARPS * R2_LS_IT * 33 * 8;
+    if (do_loss) off += R2_WARPS * R2_LS_IT * R2_LS_PITCH * 8;
     L.total = off;
     return L;
 }
@@ -522,7 +525,7 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
     double* pp = partials + (int64_t)blockIdx.z * n_tiles + tile_id;
     const int64_t pstride = (int64_t)G * n_tiles;
     const unsigned out_base = stage0 + lay.out + warp * (R2_OUT_BUFS * R2_RW * R2_TW * 8);
-    double* lsum = reinterpret_cast<double*>(smem + lay.lsum) + warp * (R2_LS_IT * 33);
+    double* lsum = reinterpret_cast<double*>(smem + lay.lsum) + warp * (R2_LS_IT * R2_LS_PITCH);
     int zc = (int)blockIdx.z;                      // chain of the current iteration
 
     // The ring loop stays ROLLED: unrolled by the stage count the kernel was 40 KB of code per variant and ran at an
@@ -577,13 +580,13 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
             // per-lane partial of this chain -> row (it mod 8) of the warp's scratch; after 8 chains the 8 x 32 block is
             // summed by all lanes (4 lanes per chain, fixed order) instead of a 5-step shuffle tree per chain
             const int row = it & (R2_LS_IT - 1);
-            lsum[row * 33 + lane] = acc;
+            lsum[row * R2_LS_PITCH + lane] = acc;
             if (row == R2_LS_IT - 1 || it == n_iter - 1) {
                 __syncwarp();
                 const int rr = lane >> 2, qd = lane & 3;
                 double t = 0.0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t = add_rn(t, lsum[rr * 33 + qd * 8 + j]);
+                for (int j = 0; j < 8; ++j) t = add_rn(t, lsum[rr * R2_LS_PITCH + qd + 4 * j]);
                 t = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
                 t = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
                 if (qd == 0 && rr <= row) pp[(int64_t)(rr - row) * pstride] = t;
