@@ -49,9 +49,15 @@
 #define R2_THREADS (R2_WARPS * 32)
 #define R2_OUT_BUFS 4                            // per-warp staging buffers of the tensor stores
 #define R2_LS_IT 8                               // loss partials are transposed through shared memory every 8 chains
+#ifdef R2_LS_OCTETS                              // A/B: the previous scratch layout (pitch 33, eight contiguous entries per lane)
+#define R2_LS_PITCH 33
+#define R2_LS_IDX(rr, qd, j) ((rr) * 33 + (qd) * 8 + (j))
+#else
+#define R2_LS_IDX(rr, qd, j) ((rr) * R2_LS_PITCH + (qd) + 4 * (j))
 #define R2_LS_PITCH 36                           // row pitch of that scratch (doubles), = 4 mod 16: lane (rr, qd) sums the entries qd + 4 j of
                                                  // row rr, so the 16 lanes of a half-warp read 16 different 8-byte banks (4 rr + qd); with
                                                  // pitch 33 and contiguous octets per lane every read was a 2-way bank conflict
+#endif
 #define R2_DIV_LO2 (2u * 0x05d00000u)            // 2 * hi word of 2^-930
 #define R2_DIV_WIN (2u * (0x7a100000u - 0x05d00000u))
 
@@ -586,7 +592,7 @@ __device__ __forceinline__ void r2_chain_loop(const CUtensorMap* tm_bed, const C
                 const int rr = lane >> 2, qd = lane & 3;
                 double t = 0.0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t = add_rn(t, lsum[rr * R2_LS_PITCH + qd + 4 * j]);
+                for (int j = 0; j < 8; ++j) t = add_rn(t, lsum[R2_LS_IDX(rr, qd, j)]);
                 t = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 1));
                 t = add_rn(t, __shfl_xor_sync(0xffffffffu, t, 2));
                 if (qd == 0 && rr <= row) pp[(int64_t)(rr - row) * pstride] = t;
